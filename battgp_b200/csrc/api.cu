@@ -1,0 +1,282 @@
+// extern "C" surface of libbattgp_b200.so (include/battgp_b200.h) and the look-ahead Cholesky driver.
+#include <climits>
+#include <cmath>
+#include <cstring>
+#include <new>
+#include "common.cuh"
+
+namespace bgp {
+
+static thread_local char g_err[512] = "";
+void set_error(const char* what, cudaError_t e) {
+    snprintf(g_err, sizeof(g_err), "%s: %s (%s)", what, cudaGetErrorName(e), cudaGetErrorString(e));
+}
+
+int cov_build(Ctx*, const bgp_kernel_spec*, const double*, int64_t, int64_t, const double*, int64_t, int64_t, double*,
+              int64_t, int, cudaStream_t);
+int cov_diag(Ctx*, const bgp_kernel_spec*, const double*, int64_t, int64_t, double*, cudaStream_t);
+int trsv_lower(Ctx*, const double*, int64_t, int64_t, const double*, double*, double*, cudaStream_t);
+int trsv_lower_t(Ctx*, const double*, int64_t, int64_t, const double*, double*, double*, cudaStream_t);
+int dot(Ctx*, const double*, const double*, int64_t, double*, double*, cudaStream_t);
+int predict_tail(Ctx*, int64_t, int64_t, const double*, int64_t, const double*, const double*, int64_t, const double*,
+                 double, double*, double*, cudaStream_t);
+int potri(Ctx*, double*, int64_t, int64_t, const double*, double*, int64_t, cudaStream_t);
+int lml_grad(Ctx*, const bgp_kernel_spec*, const double*, int64_t, int64_t, const double*, int64_t, const double*,
+             double*, cudaStream_t);
+
+__global__ void init_scalars_kernel(int32_t* info, double* scal) {
+    if (threadIdx.x == 0) { *info = INT_MAX; scal[0] = 0.0; }
+}
+
+struct DeviceGuard {
+    int prev = -1;
+    bool ok = true;
+    explicit DeviceGuard(int dev) {
+        if (cudaGetDevice(&prev) != cudaSuccess) { ok = false; return; }
+        if (prev != dev && cudaSetDevice(dev) != cudaSuccess) ok = false;
+    }
+    ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
+};
+
+// Right-looking over NB-wide panels with one panel of look-ahead (see potrf.cu header comment).
+static int potrf_driver(Ctx* ctx, double* A, int64_t n, int64_t lda, double* dinv, cudaStream_t mainst) {
+    const int64_t NB = ctx->nb;
+    if (!ctx->lookahead || n <= 2 * NB) return potrf_rec(ctx, A, n, lda, dinv, 0, mainst);
+    cudaStream_t P = ctx->panel_stream;
+    BGP_CUDA_OK(cudaEventRecord(ctx->ev_fork, mainst));
+    BGP_CUDA_OK(cudaStreamWaitEvent(P, ctx->ev_fork, 0));
+    const int64_t npanels = (n + NB - 1) / NB;
+    for (int64_t k = 0; k < npanels; k++) {
+        const int64_t k0 = k * NB;
+        const int64_t nbk = (n - k0 < NB) ? n - k0 : NB;
+        const int64_t below = n - k0 - nbk;
+        double* Akk = A + k0 * lda + k0;
+        double* dinv_k = dinv + (k0 / LEAF) * (int64_t)LEAF * LEAF;
+        int rc;
+        // ---- P_k (panel stream): bring column block k up to date with panel k-1, factor it, solve the rows below
+        if (k >= 1) {
+            if (k >= 2) BGP_CUDA_OK(cudaStreamWaitEvent(P, ctx->ev_trail[(k - 2) % 3], 0));
+            const double* Lp = A + k0 * lda + (k0 - NB);     // rows k0.., columns of panel k-1
+            GemmArgs g{Lp, lda, Lp, lda, Akk, lda, (int)(n - k0), (int)nbk, (int)NB, -1.0, 1.0, 1, 0, 0};
+            if ((rc = gemm_nt(ctx, g, P))) return rc;
+        }
+        if ((rc = potrf_rec(ctx, Akk, nbk, lda, dinv_k, k0, P))) return rc;
+        if (below > 0 && (rc = trsm_rlt_rec(ctx, Akk, nbk, lda, dinv_k, Akk + nbk * lda, below, lda, P))) return rc;
+        BGP_CUDA_OK(cudaEventRecord(ctx->ev_panel[k % 2], P));
+        // ---- T_k (caller's stream): rank-nbk update of everything right of column block k+1
+        const int64_t t0 = k0 + nbk + NB;
+        if (t0 < n) {
+            BGP_CUDA_OK(cudaStreamWaitEvent(mainst, ctx->ev_panel[k % 2], 0));
+            const double* Lt = A + t0 * lda + k0;
+            GemmArgs g{Lt, lda, Lt, lda, A + t0 * lda + t0, lda, (int)(n - t0), (int)(n - t0), (int)nbk, -1.0, 1.0, 1, 0, 0};
+            if ((rc = gemm_nt(ctx, g, mainst))) return rc;
+            BGP_CUDA_OK(cudaEventRecord(ctx->ev_trail[k % 3], mainst));
+        }
+    }
+    BGP_CUDA_OK(cudaEventRecord(ctx->ev_join, P));
+    BGP_CUDA_OK(cudaStreamWaitEvent(mainst, ctx->ev_join, 0));
+    return 0;
+}
+
+}  // namespace bgp
+
+using namespace bgp;
+
+#define CTX_OR_FAIL(c)                      \
+    if (!(c)) return BGP_E_ARG;             \
+    Ctx* ctx = reinterpret_cast<Ctx*>(c);   \
+    DeviceGuard guard__(ctx->device);       \
+    if (!guard__.ok) { set_error("cudaSetDevice", cudaGetLastError()); return BGP_E_CUDA; }
+
+extern "C" {
+
+int bgp_version(void) { return BGP_VERSION; }
+const char* bgp_last_error(void) { return g_err; }
+
+int bgp_grad_slots(const bgp_kernel_spec* s) {
+    if (!s || s->nterms < 1 || s->nterms > BGP_MAX_TERMS) return BGP_E_SPEC;
+    int slots = 1;
+    for (int t = 0; t < s->nterms; t++) {
+        const bgp_term& T = s->terms[t];
+        slots += 1;
+        if (T.type == BGP_WIENER) continue;
+        if (T.ndims < 1 || T.ndims > BGP_MAX_DIMS) return BGP_E_SPEC;
+        slots += T.ndims;
+        if (T.type == BGP_PERIODIC) slots += T.ndims;
+    }
+    return slots;
+}
+
+int bgp_ctx_create(int device, bgp_ctx** out) {
+    if (!out) return BGP_E_ARG;
+    *out = nullptr;
+    DeviceGuard guard(device);
+    if (!guard.ok) { set_error("cudaSetDevice", cudaGetLastError()); return BGP_E_CUDA; }
+    Ctx* c = new (std::nothrow) Ctx();
+    if (!c) return BGP_E_ARG;
+    c->device = device;
+    int lo = 0, hi = 0;
+    BGP_CUDA_OK(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+    BGP_CUDA_OK(cudaStreamCreateWithPriority(&c->panel_stream, cudaStreamNonBlocking, hi));
+    BGP_CUDA_OK(cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming));
+    BGP_CUDA_OK(cudaEventCreateWithFlags(&c->ev_join, cudaEventDisableTiming));
+    for (auto& e : c->ev_panel) BGP_CUDA_OK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    for (auto& e : c->ev_trail) BGP_CUDA_OK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    BGP_CUDA_OK(cudaMalloc(&c->d_info, 256));
+    BGP_CUDA_OK(cudaMalloc(&c->d_scal, 512 * sizeof(double)));
+    BGP_CUDA_OK(cudaMalloc(&c->d_scratch, SCRATCH_BYTES));
+    *out = reinterpret_cast<bgp_ctx*>(c);
+    return 0;
+}
+
+void bgp_ctx_destroy(bgp_ctx* p) {
+    if (!p) return;
+    Ctx* c = reinterpret_cast<Ctx*>(p);
+    DeviceGuard guard(c->device);
+    if (c->panel_stream) { cudaStreamSynchronize(c->panel_stream); cudaStreamDestroy(c->panel_stream); }
+    if (c->ev_fork) cudaEventDestroy(c->ev_fork);
+    if (c->ev_join) cudaEventDestroy(c->ev_join);
+    for (auto& e : c->ev_panel) if (e) cudaEventDestroy(e);
+    for (auto& e : c->ev_trail) if (e) cudaEventDestroy(e);
+    if (c->d_info) cudaFree(c->d_info);
+    if (c->d_scal) cudaFree(c->d_scal);
+    if (c->d_scratch) cudaFree(c->d_scratch);
+    delete c;
+}
+
+int bgp_ctx_set(bgp_ctx* p, const char* key, int value) {
+    if (!p || !key) return BGP_E_ARG;
+    Ctx* c = reinterpret_cast<Ctx*>(p);
+    if (!strcmp(key, "nb")) {
+        if (value < LEAF || value % LEAF != 0 || value > 8192) return BGP_E_ARG;
+        c->nb = value;
+        return 0;
+    }
+    if (!strcmp(key, "lookahead")) { c->lookahead = value ? 1 : 0; return 0; }
+    if (!strcmp(key, "gemm_cfg")) { if (value < 0 || value > 7) return BGP_E_ARG; c->gemm_cfg = value; return 0; }
+    return BGP_E_ARG;
+}
+
+int64_t bgp_ctx_launches(const bgp_ctx* p) { return p ? reinterpret_cast<const Ctx*>(p)->launches : 0; }
+
+int bgp_cov_build(bgp_ctx* c, const bgp_kernel_spec* spec, const double* X1, int64_t n1, int64_t ldx1, const double* X2,
+                  int64_t n2, int64_t ldx2, double* out, int64_t ldo, int symmetric, void* stream) {
+    CTX_OR_FAIL(c);
+    return cov_build(ctx, spec, X1, n1, ldx1, X2, n2, ldx2, out, ldo, symmetric, (cudaStream_t)stream);
+}
+
+int bgp_cov_diag(bgp_ctx* c, const bgp_kernel_spec* spec, const double* X, int64_t n, int64_t ldx, double* out,
+                 void* stream) {
+    CTX_OR_FAIL(c);
+    return cov_diag(ctx, spec, X, n, ldx, out, (cudaStream_t)stream);
+}
+
+int bgp_gemm_nt(bgp_ctx* c, int64_t M, int64_t N, int64_t K, double alpha, const double* A, int64_t lda,
+                const double* B, int64_t ldb, double beta, double* C, int64_t ldc, int tri, int64_t roff, int64_t coff,
+                void* stream) {
+    CTX_OR_FAIL(c);
+    if (M < 0 || N < 0 || K < 0 || M > INT_MAX || N > INT_MAX || K > INT_MAX) return BGP_E_ARG;
+    if (M == 0 || N == 0) return 0;
+    if (!C || ldc < N || (K > 0 && (!A || !B || lda < K || ldb < K))) return BGP_E_ARG;
+    GemmArgs g{A, lda, B, ldb, C, ldc, (int)M, (int)N, (int)K, alpha, beta, tri ? 1 : 0, roff, coff};
+    return gemm_nt(ctx, g, (cudaStream_t)stream);
+}
+
+int64_t bgp_potrf_dinv_elems(int64_t n) { return n <= 0 ? 0 : ((n + LEAF - 1) / LEAF) * (int64_t)LEAF * LEAF; }
+
+int bgp_potrf(bgp_ctx* c, double* A, int64_t n, int64_t lda, double* dinv, double* logdet_host, void* stream) {
+    CTX_OR_FAIL(c);
+    if (n < 0 || n > INT_MAX) return BGP_E_ARG;
+    if (n == 0) { if (logdet_host) *logdet_host = 0.0; return 0; }
+    if (!A || !dinv || lda < n) return BGP_E_ARG;
+    cudaStream_t st = (cudaStream_t)stream;
+    init_scalars_kernel<<<1, 32, 0, st>>>(ctx->d_info, ctx->d_scal);
+    BGP_LAUNCH_OK(ctx);
+    int rc = potrf_driver(ctx, A, n, lda, dinv, st);
+    if (rc) return rc;
+    int32_t info = 0;
+    double ld = 0.0;
+    BGP_CUDA_OK(cudaMemcpyAsync(&info, ctx->d_info, sizeof(info), cudaMemcpyDeviceToHost, st));
+    BGP_CUDA_OK(cudaMemcpyAsync(&ld, ctx->d_scal, sizeof(ld), cudaMemcpyDeviceToHost, st));
+    BGP_CUDA_OK(cudaStreamSynchronize(st));
+    if (logdet_host) *logdet_host = ld;
+    return info == INT_MAX ? 0 : (int)info;
+}
+
+int bgp_potrf_block(bgp_ctx* c, double* A, int64_t nb, int64_t lda, double* dinv, int32_t* info_dev, double* logdet_dev,
+                    void* stream) {
+    CTX_OR_FAIL(c);
+    if (!A || !dinv || nb <= 0 || lda < nb) return BGP_E_ARG;
+    // temporarily redirect the leaf outputs to the caller's device scalars
+    int32_t* si = ctx->d_info;
+    double* ss = ctx->d_scal;
+    if (info_dev) ctx->d_info = info_dev;
+    if (logdet_dev) ctx->d_scal = logdet_dev;
+    int rc = potrf_rec(ctx, A, nb, lda, dinv, 0, (cudaStream_t)stream);
+    ctx->d_info = si;
+    ctx->d_scal = ss;
+    return rc;
+}
+
+int bgp_potrs_vec(bgp_ctx* c, const double* L, int64_t n, int64_t ldl, const double* dinv, const double* y, double* z,
+                  double* alpha, void* stream) {
+    CTX_OR_FAIL(c);
+    if (n == 0) return 0;
+    if (!L || !dinv || !y || !z || !alpha || n < 0 || ldl < n) return BGP_E_ARG;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (z != y) BGP_CUDA_OK(cudaMemcpyAsync(z, y, n * sizeof(double), cudaMemcpyDeviceToDevice, st));
+    int rc = trsv_lower(ctx, L, n, ldl, dinv, z, z, st);
+    if (rc) return rc;
+    BGP_CUDA_OK(cudaMemcpyAsync(alpha, z, n * sizeof(double), cudaMemcpyDeviceToDevice, st));
+    return trsv_lower_t(ctx, L, n, ldl, dinv, alpha, alpha, st);
+}
+
+int bgp_trsm_rlt(bgp_ctx* c, const double* L, int64_t n, int64_t ldl, const double* dinv, double* X, int64_t m,
+                 int64_t ldx, void* stream) {
+    CTX_OR_FAIL(c);
+    if (n == 0 || m == 0) return 0;
+    if (!L || !dinv || !X || n < 0 || m < 0 || ldl < n || ldx < n || m > INT_MAX) return BGP_E_ARG;
+    return trsm_rlt_rec(ctx, L, n, ldl, dinv, X, m, ldx, (cudaStream_t)stream);
+}
+
+int bgp_predict_tail(bgp_ctx* c, int64_t m, int64_t n, const double* Kq, int64_t ldk, const double* alpha,
+                     const double* V, int64_t ldv, const double* kdiag, double min_var, double* mean, double* var,
+                     void* stream) {
+    CTX_OR_FAIL(c);
+    if (m < 0 || n < 0) return BGP_E_ARG;
+    if (mean && (!Kq || !alpha || ldk < n)) return BGP_E_ARG;
+    if (var && (!V || !kdiag || ldv < n)) return BGP_E_ARG;
+    return predict_tail(ctx, m, n, Kq, ldk, alpha, V, ldv, kdiag, min_var, mean, var, (cudaStream_t)stream);
+}
+
+int bgp_lml(bgp_ctx* c, const double* z, int64_t n, double logdet, double* lml_host, void* stream) {
+    CTX_OR_FAIL(c);
+    if (!lml_host || n < 0 || (n > 0 && !z)) return BGP_E_ARG;
+    double zz = 0.0;
+    if (n > 0) {
+        cudaStream_t st = (cudaStream_t)stream;
+        int rc = dot(ctx, z, z, n, ctx->d_scal + 8, ctx->d_scal + 1, st);
+        if (rc) return rc;
+        BGP_CUDA_OK(cudaMemcpyAsync(&zz, ctx->d_scal + 1, sizeof(double), cudaMemcpyDeviceToHost, st));
+        BGP_CUDA_OK(cudaStreamSynchronize(st));
+    }
+    *lml_host = -0.5 * zz - 0.5 * logdet - 0.5 * (double)n * log(2.0 * M_PI);
+    return 0;
+}
+
+int bgp_potri(bgp_ctx* c, double* L, int64_t n, int64_t ldl, const double* dinv, double* work, int64_t ldw,
+              void* stream) {
+    CTX_OR_FAIL(c);
+    if (n == 0) return 0;
+    if (!L || !dinv || !work || n < 0 || ldl < n || ldw < n || n > INT_MAX) return BGP_E_ARG;
+    return potri(ctx, L, n, ldl, dinv, work, ldw, (cudaStream_t)stream);
+}
+
+int bgp_lml_grad(bgp_ctx* c, const bgp_kernel_spec* spec, const double* X, int64_t n, int64_t ldx, const double* Kinv,
+                 int64_t ldk, const double* alpha, double* grad_dev, void* stream) {
+    CTX_OR_FAIL(c);
+    if (!spec || !grad_dev || n < 0 || (n > 0 && (!X || !Kinv || !alpha || ldk < n))) return BGP_E_ARG;
+    return lml_grad(ctx, spec, X, n, ldx, Kinv, ldk, alpha, grad_dev, (cudaStream_t)stream);
+}
+
+}  // extern "C"

@@ -1,0 +1,64 @@
+// Shared declarations for the battgp_b200 CUDA engine (sm_100a, fp64).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include "../../include/battgp_b200.h"
+
+namespace bgp {
+
+constexpr int LEAF = 128;
+constexpr size_t SCRATCH_BYTES = 4u << 20;          // diagonal-block size of the leaf factorisation / stored inverses
+
+struct Ctx {
+    int device = 0;
+    cudaStream_t panel_stream = nullptr;    // high priority: panel factorisation (look-ahead)
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+    cudaEvent_t ev_panel[2] = {nullptr, nullptr};
+    cudaEvent_t ev_trail[3] = {nullptr, nullptr, nullptr};
+    int32_t* d_info = nullptr;              // first failing pivot (1-based), INT_MAX when none
+    double* d_scal = nullptr;               // [0] logdet accumulator, [1] dot result, [8..] dot partials
+    double* d_scratch = nullptr;            // SCRATCH_BYTES of reduction partials (lml_grad)
+    int nb = 1024;
+    int lookahead = 1;
+    int gemm_cfg = 0;                       // 0 = default big-tile config, else forced variant (probing)
+    int64_t launches = 0;
+};
+
+void set_error(const char* what, cudaError_t e);
+
+#define BGP_CUDA_OK(call)                                                                   \
+    do {                                                                                    \
+        cudaError_t e__ = (call);                                                           \
+        if (e__ != cudaSuccess) { ::bgp::set_error(#call, e__); return BGP_E_CUDA; }        \
+    } while (0)
+
+#define BGP_LAUNCH_OK(ctx)                                                                  \
+    do {                                                                                    \
+        (ctx)->launches++;                                                                  \
+        cudaError_t e__ = cudaGetLastError();                                               \
+        if (e__ != cudaSuccess) { ::bgp::set_error("kernel launch", e__); return BGP_E_CUDA; } \
+    } while (0)
+
+// ---- gemm_nt.cu
+struct GemmArgs {
+    const double* A; int64_t lda;
+    const double* B; int64_t ldb;
+    double* C; int64_t ldc;
+    int M, N, K;
+    double alpha, beta;
+    int tri;                 // 0: full; 1: only (col + coff) <= (row + roff)
+    int64_t roff, coff;
+    int kskip = 0;           // 1: A[i][k] == 0 for k < i + kofs (A upper-triangular): start K at the tile's first row
+    int64_t kofs = 0;
+};
+int gemm_nt(Ctx* ctx, const GemmArgs& g, cudaStream_t st);
+// cfg: 0 auto, 1 = 128x128 tiles, 2 = 64x128 (C may alias A when N <= 128), 3 = 64x64
+int gemm_nt_cfg(Ctx* ctx, const GemmArgs& g, int cfg, cudaStream_t st);
+
+// ---- potrf.cu
+int potrf_rec(Ctx* ctx, double* A, int64_t n, int64_t lda, double* dinv, int64_t gofs, cudaStream_t st);
+int trsm_rlt_rec(Ctx* ctx, const double* L, int64_t n, int64_t ldl, const double* dinv, double* X, int64_t m,
+                 int64_t ldx, cudaStream_t st);
+
+}  // namespace bgp

@@ -1,0 +1,232 @@
+// K5 / K6 / K8: the HBM-bound O(N^2) tail of the fit -- alpha = L^-T L^-1 y by two blocked triangular sweeps
+// (each reads L once), the predictive mean / variance reductions and the dot product for the LML.
+//
+// Forward sweep, block k (128 rows):  x_k = inv(L_kk) b_k ;  b[k+1:] -= L[k+1:, k] x_k
+// One launch per block: every CTA updates 128 rows of b with coalesced row-dot-products against x_k; CTA 0 owns
+// the rows of block k+1 and, once they are final, also applies inv(L_{k+1,k+1}) so the next launch finds x_{k+1}
+// ready.  Backward sweep is the mirror image on L^T (column sums over the row-block of L, coalesced along columns).
+#include "common.cuh"
+
+namespace bgp {
+
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+// x[0:nb] = Dinv[0:nb,0:nb] * b[0:nb]   (first block of the forward sweep), one CTA of 256 threads
+__global__ void __launch_bounds__(256) trsv_first_kernel(const double* __restrict__ dinv, const double* __restrict__ b,
+                                                         double* __restrict__ x, int nb) {
+    __shared__ double sb[LEAF];
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    if (tid < LEAF) sb[tid] = tid < nb ? b[tid] : 0.0;
+    __syncthreads();
+    for (int r = warp; r < nb; r += 8) {
+        double s = 0.0;
+        for (int c = lane; c <= r; c += 32) s = fma(dinv[r * LEAF + c], sb[c], s);
+        s = warp_sum(s);
+        if (lane == 0) x[r] = s;
+    }
+}
+
+// forward step for block k (rows k0..k0+nbk-1 solved, x holds x_k at x[k0..]):
+//   rows i >= k0+nbk:  b[i] -= L[i, k0:k0+nbk] . x_k ;  CTA 0 then x[k0+nbk ..] = Dinv_{k+1} * b[k0+nbk ..]
+__global__ void __launch_bounds__(256)
+trsv_fwd_step_kernel(const double* __restrict__ L, int64_t ldl, int64_t n, int64_t k0, int nbk,
+                     const double* __restrict__ dinv_next, double* b, double* x) {
+    __shared__ double sx[LEAF];
+    __shared__ double sb[LEAF];
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    if (tid < LEAF) sx[tid] = tid < nbk ? x[k0 + tid] : 0.0;
+    __syncthreads();
+    const int64_t r0 = k0 + nbk + (int64_t)blockIdx.x * LEAF;
+    const double x0 = sx[lane], x1 = sx[lane + 32], x2 = sx[lane + 64], x3 = sx[lane + 96];
+    // 16 rows per warp, 4 at a time for memory-level parallelism
+    for (int rr = 0; rr < 16; rr += 4) {
+        double s[4];
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+            const int64_t row = r0 + warp * 16 + rr + u;
+            s[u] = 0.0;
+            if (row < n) {
+                const double* lp = L + row * ldl + k0;
+                double a0 = lane < nbk ? lp[lane] : 0.0;
+                double a1 = lane + 32 < nbk ? lp[lane + 32] : 0.0;
+                double a2 = lane + 64 < nbk ? lp[lane + 64] : 0.0;
+                double a3 = lane + 96 < nbk ? lp[lane + 96] : 0.0;
+                s[u] = a0 * x0 + a1 * x1 + a2 * x2 + a3 * x3;
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+            const int64_t row = r0 + warp * 16 + rr + u;
+            const double t = warp_sum(s[u]);
+            if (row < n) {
+                const double nb_ = b[row] - t;
+                if (lane == 0) b[row] = nb_;
+                if (blockIdx.x == 0) sb[warp * 16 + rr + u] = nb_;
+            }
+        }
+    }
+    if (blockIdx.x != 0) return;
+    __syncthreads();
+    const int nnext = (int)min((int64_t)LEAF, n - r0);
+    for (int r = warp; r < nnext; r += 8) {
+        double s = 0.0;
+        for (int c = lane; c <= r; c += 32) s = fma(dinv_next[r * LEAF + c], sb[c], s);
+        s = warp_sum(s);
+        if (lane == 0) x[r0 + r] = s;
+    }
+}
+
+// x[k0 + i] = sum_r Dinv[r][i] * b[k0 + r]   (last block of the backward sweep = first to be solved)
+__global__ void __launch_bounds__(128) trsv_last_kernel(const double* __restrict__ dinv, const double* __restrict__ b,
+                                                        double* __restrict__ x, int nb) {
+    __shared__ double sb[LEAF];
+    const int tid = threadIdx.x;
+    sb[tid] = tid < nb ? b[tid] : 0.0;
+    __syncthreads();
+    if (tid < nb) {
+        double s = 0.0;
+        for (int r = tid; r < nb; r++) s = fma(dinv[r * LEAF + tid], sb[r], s);
+        x[tid] = s;
+    }
+}
+
+// backward step for block k (x_k at x[k0..k0+nbk-1] solved): columns c < k0:  b[c] -= sum_r L[k0+r][c] x_k[r];
+// CTA 0 owns the 128 columns just left of k0 and then applies inv(L_{k-1,k-1})^T.
+// 256 threads = 128 columns x 2 row-halves.
+__global__ void __launch_bounds__(256)
+trsv_bwd_step_kernel(const double* __restrict__ L, int64_t ldl, int64_t k0, int nbk,
+                     const double* __restrict__ dinv_prev, double* b, double* x) {
+    __shared__ double sx[LEAF];
+    __shared__ double part[LEAF];
+    __shared__ double sb[LEAF];
+    const int tid = threadIdx.x;
+    if (tid < LEAF) sx[tid] = tid < nbk ? x[k0 + tid] : 0.0;
+    __syncthreads();
+    const int cl = tid & (LEAF - 1), half = tid >> 7;
+    const int64_t c = k0 - LEAF - (int64_t)blockIdx.x * LEAF + cl;   // CTA 0: columns k0-128 .. k0-1
+    double s = 0.0;
+    if (c >= 0) {
+        const double* lp = L + (k0 + half * 64) * ldl + c;
+        const int rend = min(64, nbk - half * 64);
+#pragma unroll 8
+        for (int r = 0; r < rend; r++) s = fma(lp[(int64_t)r * ldl], sx[half * 64 + r], s);
+    }
+    if (half == 1) part[cl] = s;
+    __syncthreads();
+    double nbv = 0.0;
+    if (half == 0 && c >= 0) {
+        nbv = b[c] - (s + part[cl]);
+        b[c] = nbv;
+    }
+    if (blockIdx.x != 0) return;
+    if (half == 0) sb[cl] = nbv;
+    __syncthreads();
+    // x_{k-1}[i] = sum_{r >= i} DinvPrev[r][i] * b_{k-1}[r]   (block k-1 is always a full 128 block)
+    if (tid < LEAF) {
+        double t = 0.0;
+        for (int r = tid; r < LEAF; r++) t = fma(dinv_prev[r * LEAF + tid], sb[r], t);
+        x[k0 - LEAF + tid] = t;
+    }
+}
+
+int trsv_lower(Ctx* ctx, const double* L, int64_t n, int64_t ldl, const double* dinv, double* b, double* x,
+               cudaStream_t st) {
+    // solves L x = b; b is destroyed (holds the updated right-hand side)
+    const int64_t nblk = (n + LEAF - 1) / LEAF;
+    trsv_first_kernel<<<1, 256, 0, st>>>(dinv, b, x, (int)min((int64_t)LEAF, n));
+    BGP_LAUNCH_OK(ctx);
+    for (int64_t k = 0; k + 1 < nblk; k++) {
+        const int64_t k0 = k * LEAF;
+        const int64_t rows = n - k0 - LEAF;
+        const unsigned grid = (unsigned)((rows + LEAF - 1) / LEAF);
+        trsv_fwd_step_kernel<<<grid, 256, 0, st>>>(L, ldl, n, k0, LEAF, dinv + (k + 1) * (int64_t)LEAF * LEAF, b, x);
+        BGP_LAUNCH_OK(ctx);
+    }
+    return 0;
+}
+
+int trsv_lower_t(Ctx* ctx, const double* L, int64_t n, int64_t ldl, const double* dinv, double* b, double* x,
+                 cudaStream_t st) {
+    // solves L^T x = b; b is destroyed
+    const int64_t nblk = (n + LEAF - 1) / LEAF;
+    const int64_t kl = (nblk - 1) * LEAF;
+    const int nbl = (int)(n - kl);
+    trsv_last_kernel<<<1, 128, 0, st>>>(dinv + (nblk - 1) * (int64_t)LEAF * LEAF, b + kl, x + kl, nbl);
+    BGP_LAUNCH_OK(ctx);
+    for (int64_t k = nblk - 1; k >= 1; k--) {
+        const int64_t k0 = k * LEAF;
+        const int nbk = (int)min((int64_t)LEAF, n - k0);
+        const unsigned grid = (unsigned)(k0 / LEAF);
+        trsv_bwd_step_kernel<<<grid, 256, 0, st>>>(L, ldl, k0, nbk, dinv + (k - 1) * (int64_t)LEAF * LEAF, b, x);
+        BGP_LAUNCH_OK(ctx);
+    }
+    return 0;
+}
+
+// mean[i] = Kq[i,:] . alpha ;  var[i] = max(kdiag[i] - |V[i,:]|^2, min_var).  One CTA per query row.
+__global__ void __launch_bounds__(256)
+predict_tail_kernel(int64_t n, const double* __restrict__ Kq, int64_t ldk, const double* __restrict__ alpha,
+                    const double* __restrict__ V, int64_t ldv, const double* __restrict__ kdiag, double min_var,
+                    double* __restrict__ mean, double* __restrict__ var) {
+    __shared__ double red[2][8];
+    const int64_t i = blockIdx.x;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    double sm = 0.0, sv = 0.0;
+    if (mean) {
+        const double* kp = Kq + i * ldk;
+        for (int64_t j = tid; j < n; j += 256) sm = fma(kp[j], alpha[j], sm);
+    }
+    if (var) {
+        const double* vp = V + i * ldv;
+        for (int64_t j = tid; j < n; j += 256) { const double v = vp[j]; sv = fma(v, v, sv); }
+    }
+    sm = warp_sum(sm);
+    sv = warp_sum(sv);
+    if (lane == 0) { red[0][warp] = sm; red[1][warp] = sv; }
+    __syncthreads();
+    if (tid == 0) {
+        double a = 0.0, b = 0.0;
+        for (int w = 0; w < 8; w++) { a += red[0][w]; b += red[1][w]; }
+        if (mean) mean[i] = a;
+        if (var) var[i] = fmax(kdiag[i] - b, min_var);
+    }
+}
+
+// deterministic two-stage dot product: partial[blockIdx] then a single-CTA finish into out[0]
+__global__ void __launch_bounds__(256) dot_partial_kernel(const double* __restrict__ a, const double* __restrict__ b,
+                                                          int64_t n, double* __restrict__ partial) {
+    __shared__ double red[8];
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    double s = 0.0;
+    for (int64_t j = (int64_t)blockIdx.x * 256 + tid; j < n; j += (int64_t)gridDim.x * 256) s = fma(a[j], b[j], s);
+    s = warp_sum(s);
+    if (lane == 0) red[warp] = s;
+    __syncthreads();
+    if (tid == 0) { double t = 0.0; for (int w = 0; w < 8; w++) t += red[w]; partial[blockIdx.x] = t; }
+}
+__global__ void dot_finish_kernel(const double* __restrict__ partial, int np, double* __restrict__ out) {
+    if (threadIdx.x == 0) { double t = 0.0; for (int i = 0; i < np; i++) t += partial[i]; out[0] = t; }
+}
+
+int dot(Ctx* ctx, const double* a, const double* b, int64_t n, double* partial /*>=128*/, double* out, cudaStream_t st) {
+    const int np = (int)min((int64_t)128, (n + 255) / 256 > 0 ? (n + 255) / 256 : 1);
+    dot_partial_kernel<<<np, 256, 0, st>>>(a, b, n, partial);
+    BGP_LAUNCH_OK(ctx);
+    dot_finish_kernel<<<1, 32, 0, st>>>(partial, np, out);
+    BGP_LAUNCH_OK(ctx);
+    return 0;
+}
+
+int predict_tail(Ctx* ctx, int64_t m, int64_t n, const double* Kq, int64_t ldk, const double* alpha, const double* V,
+                 int64_t ldv, const double* kdiag, double min_var, double* mean, double* var, cudaStream_t st) {
+    if (m <= 0) return 0;
+    predict_tail_kernel<<<(unsigned)m, 256, 0, st>>>(n, Kq, ldk, alpha, V, ldv, kdiag, min_var, mean, var);
+    BGP_LAUNCH_OK(ctx);
+    return 0;
+}
+
+}  // namespace bgp

@@ -1,0 +1,341 @@
+"""Tensor-level host side of the B200 exact-GP engine: torch owns memory and streams, every FLOP of the path runs in
+libbattgp_b200.so through the C-ABI (include/battgp_b200.h).  No CPU fallback, nothing imported from ``oracle/``.
+
+Mirrors what GPyTorch executes for BattGP's ``full_gp`` mode under the Cholesky path:
+  fit      = ExactGP prediction-strategy set-up / ExactMarginalLogLikelihood
+             (/root/reference/src/batt_models/battcellgp_full.py:173, /root/reference/src/gp/training.py:40)
+  predict  = MultivariateNormal.mean / .variance of the latent f (battcellgp_full.py:175-180)
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+import warnings
+from dataclasses import dataclass, field
+from typing import Optional, Sequence
+
+import torch
+
+from . import _lib
+from ._lib import MATERN52, PERIODIC, RBF, WIENER, BgpKernelSpec
+
+MIN_VARIANCE_F64 = 1e-10      # gpytorch.settings.min_variance for fp64
+JITTERS_F64 = (1e-8, 1e-7, 1e-6)  # psd_safe_cholesky retries
+
+
+class NotPSDError(RuntimeError):
+    """Cholesky failed even after the jitter retries (GPyTorch: linear_operator.utils.errors.NotPSDError)."""
+
+
+class NanError(RuntimeError):
+    """NaN encountered in the covariance matrix (GPyTorch: linear_operator.utils.errors.NanError)."""
+
+
+class NumericalWarning(RuntimeWarning):
+    """gpytorch.utils.warnings.NumericalWarning (silenced by /root/reference/gp_runner.py:28)."""
+
+
+@dataclass
+class Term:
+    """One ``ScaleKernel(base)`` summand; ``dims`` = GPyTorch ``active_dims``."""
+    type: int
+    dims: Sequence[int]
+    outputscale: float
+    lengthscale: Sequence[float] = ()
+    period: Sequence[float] = ()
+
+
+@dataclass
+class KernelSpec:
+    terms: list = field(default_factory=list)
+
+    def to_c(self, noise: float = 0.0) -> BgpKernelSpec:
+        if not 1 <= len(self.terms) <= _lib.MAX_TERMS:
+            raise ValueError(f"1..{_lib.MAX_TERMS} kernel terms supported, got {len(self.terms)}")
+        s = BgpKernelSpec()
+        s.nterms = len(self.terms)
+        s.noise = float(noise)
+        for i, t in enumerate(self.terms):
+            ct = s.terms[i]
+            ct.type = int(t.type)
+            dims = list(t.dims)
+            if len(dims) > _lib.MAX_DIMS or len(dims) < 1:
+                raise ValueError("1..8 active dims per term")
+            ct.ndims = len(dims)
+            for k, d in enumerate(dims):
+                ct.dims[k] = int(d)
+            ct.outputscale = float(t.outputscale)
+            ls = list(t.lengthscale)
+            if t.type != WIENER:
+                if len(ls) == 1 and len(dims) > 1:
+                    ls = ls * len(dims)
+                if len(ls) != len(dims):
+                    raise ValueError("lengthscale must have one entry per active dim")
+            for k, v in enumerate(ls[: _lib.MAX_DIMS]):
+                ct.lengthscale[k] = float(v)
+            per = list(t.period)
+            if t.type == PERIODIC:
+                if len(per) == 1 and len(dims) > 1:
+                    per = per * len(dims)
+                if len(per) != len(dims):
+                    raise ValueError("period must have one entry per active dim")
+            for k, v in enumerate(per[: _lib.MAX_DIMS]):
+                ct.period[k] = float(v)
+        return s
+
+
+def battgp_spec(outputscale_wiener=4.23e-13, outputscale_rbf=0.0099, lengthscale_rbf=(12.11, 33.75, 45.14)) -> KernelSpec:
+    """cell_gp.py:32-36 with the config.py:39-43 defaults."""
+    return KernelSpec([Term(WIENER, [0], outputscale_wiener), Term(RBF, [1, 2, 3], outputscale_rbf, tuple(lengthscale_rbf))])
+
+
+def scaled_rbf_spec(d: int, outputscale: float, lengthscale: float) -> KernelSpec:
+    """standard_models.py:24."""
+    return KernelSpec([Term(RBF, list(range(d)), outputscale, (lengthscale,) * d)])
+
+
+def matern_periodic_spec(s_m=0.0099, ls=(12.11, 33.75, 45.14), s_p=1e-4, period=1.0, ls_p=1.0) -> KernelSpec:
+    """BASELINE.json config 3."""
+    return KernelSpec([Term(MATERN52, [1, 2, 3], s_m, tuple(ls)), Term(PERIODIC, [0], s_p, (ls_p,), (period,))])
+
+
+def _ptr(t: Optional[torch.Tensor]):
+    return C.c_void_p(t.data_ptr()) if t is not None else C.c_void_p(0)
+
+
+def _check_f64_cuda(t: torch.Tensor, name: str, device: torch.device):
+    if t.dtype != torch.float64:
+        raise TypeError(f"{name}: expected float64, got {t.dtype}")
+    if t.device != device:
+        raise ValueError(f"{name}: expected device {device}, got {t.device}")
+
+
+def alloc_matrix(rows: int, cols: int, device) -> torch.Tensor:
+    """rows x cols fp64 view with an even leading dimension (16-byte aligned rows for cp.async / vector stores)."""
+    ld = cols + (cols & 1)
+    return torch.empty((rows, ld), dtype=torch.float64, device=device)[:, :cols]
+
+
+class Engine:
+    """One per CUDA device (one process per GPU in the reference's deployment, gp_runner.py:150-171)."""
+
+    def __init__(self, device):
+        self.device = torch.device(device)
+        if self.device.type != "cuda":
+            raise _lib.BattGPLibraryError("battgp_b200 runs on CUDA devices only (no CPU fallback)")
+        if self.device.index is None:
+            self.device = torch.device("cuda", torch.cuda.current_device())
+        self.L = _lib.lib()
+        torch.cuda.init()
+        h = C.c_void_p()
+        _lib.check(self.L.bgp_ctx_create(self.device.index, C.byref(h)), "bgp_ctx_create")
+        self.h = h
+
+    def __del__(self):
+        try:
+            if getattr(self, "h", None):
+                self.L.bgp_ctx_destroy(self.h)
+                self.h = None
+        except Exception:
+            pass
+
+    # ------------------------------------------------------------------ helpers
+    def _stream(self):
+        return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+
+    def set(self, key: str, value: int):
+        _lib.check(self.L.bgp_ctx_set(self.h, key.encode(), int(value)), f"bgp_ctx_set({key})")
+
+    @property
+    def launches(self) -> int:
+        return int(self.L.bgp_ctx_launches(self.h))
+
+    @staticmethod
+    def _ld(t: torch.Tensor) -> int:
+        if t.dim() != 2 or (t.shape[1] > 1 and t.stride(1) != 1):
+            raise ValueError("expected a row-major 2-D tensor")
+        return t.stride(0) if t.shape[0] > 1 else max(t.stride(0), t.shape[1])
+
+    # ------------------------------------------------------------------ K1-K3
+    def cov_build(self, spec: KernelSpec, x1: torch.Tensor, x2: Optional[torch.Tensor] = None, *, noise: float = 0.0,
+                  symmetric: bool = False, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+        _check_f64_cuda(x1, "x1", self.device)
+        x1 = x1.contiguous() if x1.stride(-1) != 1 else x1
+        if symmetric:
+            x2 = x1
+        else:
+            if x2 is None:
+                raise ValueError("x2 required unless symmetric")
+            _check_f64_cuda(x2, "x2", self.device)
+            x2 = x2.contiguous() if x2.stride(-1) != 1 else x2
+        n1, n2 = x1.shape[0], x2.shape[0]
+        if out is None:
+            out = alloc_matrix(n1, n2, self.device)
+        cs = spec.to_c(noise)
+        rc = self.L.bgp_cov_build(self.h, C.byref(cs), _ptr(x1), n1, self._ld(x1), _ptr(x2), n2, self._ld(x2),
+                                  _ptr(out), self._ld(out), 1 if symmetric else 0, self._stream())
+        _lib.check(rc, "bgp_cov_build")
+        return out
+
+    def cov_diag(self, spec: KernelSpec, x: torch.Tensor) -> torch.Tensor:
+        _check_f64_cuda(x, "x", self.device)
+        x = x.contiguous() if x.stride(-1) != 1 else x
+        out = torch.empty(x.shape[0], dtype=torch.float64, device=self.device)
+        cs = spec.to_c(0.0)
+        _lib.check(self.L.bgp_cov_diag(self.h, C.byref(cs), _ptr(x), x.shape[0], self._ld(x), _ptr(out), self._stream()),
+                   "bgp_cov_diag")
+        return out
+
+    # ------------------------------------------------------------------ dense block
+    def gemm_nt(self, A: torch.Tensor, B: torch.Tensor, C_: torch.Tensor, alpha=1.0, beta=0.0, tri=False, roff=0, coff=0):
+        M, K = A.shape
+        N = B.shape[0]
+        assert B.shape[1] == K and C_.shape == (M, N)
+        rc = self.L.bgp_gemm_nt(self.h, M, N, K, float(alpha), _ptr(A), self._ld(A), _ptr(B), self._ld(B), float(beta),
+                                _ptr(C_), self._ld(C_), 1 if tri else 0, roff, coff, self._stream())
+        _lib.check(rc, "bgp_gemm_nt")
+        return C_
+
+    # ------------------------------------------------------------------ K4
+    def potrf(self, A: torch.Tensor):
+        """In-place lower Cholesky.  Returns (info, logdet, dinv)."""
+        _check_f64_cuda(A, "A", self.device)
+        n = A.shape[0]
+        dinv = torch.empty(int(self.L.bgp_potrf_dinv_elems(n)), dtype=torch.float64, device=self.device)
+        logdet = C.c_double(0.0)
+        rc = self.L.bgp_potrf(self.h, _ptr(A), n, self._ld(A), _ptr(dinv), C.byref(logdet), self._stream())
+        _lib.check(rc, "bgp_potrf")
+        return rc, logdet.value, dinv
+
+    # ------------------------------------------------------------------ K5
+    def potrs_vec(self, Lm: torch.Tensor, dinv: torch.Tensor, y: torch.Tensor):
+        n = Lm.shape[0]
+        _check_f64_cuda(y, "y", self.device)
+        y = y.contiguous()
+        z = torch.empty(n, dtype=torch.float64, device=self.device)
+        alpha = torch.empty(n, dtype=torch.float64, device=self.device)
+        rc = self.L.bgp_potrs_vec(self.h, _ptr(Lm), n, self._ld(Lm), _ptr(dinv), _ptr(y), _ptr(z), _ptr(alpha),
+                                  self._stream())
+        _lib.check(rc, "bgp_potrs_vec")
+        return z, alpha
+
+    # ------------------------------------------------------------------ K7
+    def trsm_rlt(self, Lm: torch.Tensor, dinv: torch.Tensor, X: torch.Tensor) -> torch.Tensor:
+        """X <- X L^-T in place (rows of X are the right-hand sides)."""
+        n = Lm.shape[0]
+        assert X.shape[1] == n
+        rc = self.L.bgp_trsm_rlt(self.h, _ptr(Lm), n, self._ld(Lm), _ptr(dinv), _ptr(X), X.shape[0], self._ld(X),
+                                 self._stream())
+        _lib.check(rc, "bgp_trsm_rlt")
+        return X
+
+    def predict_tail(self, Kq=None, alpha=None, V=None, kdiag=None, min_var=MIN_VARIANCE_F64):
+        ref = Kq if Kq is not None else V
+        m, n = ref.shape
+        mean = torch.empty(m, dtype=torch.float64, device=self.device) if Kq is not None else None
+        var = torch.empty(m, dtype=torch.float64, device=self.device) if V is not None else None
+        rc = self.L.bgp_predict_tail(self.h, m, n, _ptr(Kq), self._ld(Kq) if Kq is not None else 0, _ptr(alpha),
+                                     _ptr(V), self._ld(V) if V is not None else 0, _ptr(kdiag), float(min_var),
+                                     _ptr(mean), _ptr(var), self._stream())
+        _lib.check(rc, "bgp_predict_tail")
+        return mean, var
+
+    # ------------------------------------------------------------------ K8
+    def lml(self, z: torch.Tensor, logdet: float) -> float:
+        out = C.c_double(0.0)
+        _lib.check(self.L.bgp_lml(self.h, _ptr(z), z.shape[0], float(logdet), C.byref(out), self._stream()), "bgp_lml")
+        return out.value
+
+    # ------------------------------------------------------------------ K9
+    def potri(self, Lm: torch.Tensor, dinv: torch.Tensor, work: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """L (lower, in place) -> K^-1 (lower triangle of the same storage)."""
+        n = Lm.shape[0]
+        if work is None:
+            work = alloc_matrix(n, n, self.device)
+        rc = self.L.bgp_potri(self.h, _ptr(Lm), n, self._ld(Lm), _ptr(dinv), _ptr(work), self._ld(work), self._stream())
+        _lib.check(rc, "bgp_potri")
+        return Lm
+
+    def lml_grad(self, spec: KernelSpec, noise: float, x: torch.Tensor, Kinv: torch.Tensor, alpha: torch.Tensor):
+        cs = spec.to_c(noise)
+        slots = _lib.check(self.L.bgp_grad_slots(C.byref(cs)), "bgp_grad_slots")
+        g = torch.empty(slots, dtype=torch.float64, device=self.device)
+        x = x.contiguous() if x.stride(-1) != 1 else x
+        rc = self.L.bgp_lml_grad(self.h, C.byref(cs), _ptr(x), x.shape[0], self._ld(x), _ptr(Kinv), self._ld(Kinv),
+                                 _ptr(alpha), _ptr(g), self._stream())
+        _lib.check(rc, "bgp_lml_grad")
+        return g
+
+
+_engines: dict = {}
+
+
+def get_engine(device) -> Engine:
+    device = torch.device(device)
+    if device.type != "cuda":
+        raise _lib.BattGPLibraryError(
+            f"battgp_b200 needs a CUDA device (got {device}); there is no CPU fallback for the exact-GP path")
+    idx = device.index if device.index is not None else torch.cuda.current_device()
+    if idx not in _engines:
+        _engines[idx] = Engine(torch.device("cuda", idx))
+    return _engines[idx]
+
+
+# ---------------------------------------------------------------------------------------------------------------
+@dataclass
+class FitState:
+    """What GPyTorch's DefaultPredictionStrategy caches: L (as the lower triangle of the K buffer) and alpha."""
+    spec: KernelSpec
+    noise: float
+    x: torch.Tensor
+    L: torch.Tensor
+    dinv: torch.Tensor
+    alpha: torch.Tensor
+    z: torch.Tensor
+    logdet: float
+    lml: float
+    jitter: float = 0.0
+
+
+def fit(spec: KernelSpec, x: torch.Tensor, y: torch.Tensor, noise: float, *, K_out: Optional[torch.Tensor] = None,
+        kbuilder=None) -> FitState:
+    """build K -> Cholesky (with GPyTorch's jitter retries) -> alpha -> LML.  ``kbuilder(out, extra_noise)`` may
+    replace the fused build for kernels the engine does not know (it must fill the lower triangle of ``out``)."""
+    eng = get_engine(x.device)
+    n = x.shape[0]
+    K = K_out if K_out is not None else alloc_matrix(n, n, x.device)
+    jitter = 0.0
+    for attempt in range(len(JITTERS_F64) + 1):
+        if kbuilder is None:
+            eng.cov_build(spec, x, noise=noise + jitter, symmetric=True, out=K)
+        else:
+            kbuilder(K, noise + jitter)
+        info, logdet, dinv = eng.potrf(K)
+        if info == 0 and math.isfinite(logdet):
+            break
+        if info == 0 and not math.isfinite(logdet):
+            raise NanError("cholesky: NaN/inf encountered in the covariance matrix")
+        if attempt == len(JITTERS_F64):
+            raise NotPSDError(f"Matrix not positive definite after repeatedly adding jitter up to {jitter:.1e} "
+                              f"(first failing pivot {info}).")
+        jitter = JITTERS_F64[attempt]
+        warnings.warn(f"A not p.d., added jitter of {jitter:.1e} to the diagonal", NumericalWarning)
+    z, alpha = eng.potrs_vec(K, dinv, y)
+    lml = eng.lml(z, logdet)
+    return FitState(spec, noise, x, K, dinv, alpha, z, logdet, lml, jitter)
+
+
+def predict(st: FitState, xq: torch.Tensor, *, full_cov: bool = False, clamp: bool = True, kcross=None, kdiag=None):
+    """Latent-f posterior mean and variance (no noise added): battcellgp_full.py:168-195, recursive_gp.py:120."""
+    eng = get_engine(st.x.device)
+    Kq = eng.cov_build(st.spec, xq, st.x) if kcross is None else kcross
+    mean, _ = eng.predict_tail(Kq=Kq, alpha=st.alpha)
+    V = eng.trsm_rlt(st.L, st.dinv, Kq)          # in place: Kq now holds K_*N L^-T
+    if full_cov:
+        m = xq.shape[0]
+        Cq = eng.cov_build(st.spec, xq, xq) if kdiag is None else kdiag
+        eng.gemm_nt(V, V, Cq, alpha=-1.0, beta=1.0)
+        return mean, Cq
+    kd = eng.cov_diag(st.spec, xq) if kdiag is None else kdiag
+    _, var = eng.predict_tail(V=V, kdiag=kd, min_var=MIN_VARIANCE_F64 if clamp else -math.inf)
+    return mean, var

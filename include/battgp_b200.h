@@ -1,0 +1,152 @@
+/*
+ * battgp_b200 -- C-ABI of the B200-native exact-GP engine (fp64, sm_100a).
+ *
+ * This is the drop-in boundary for BattGP's `full_gp` hot path.  The reference has NO FFI: its hot path is
+ * Python calling GPyTorch.  Each entry point below therefore cites the reference *call site*
+ * (file:line under /root/reference) whose GPyTorch work it replaces; the Python facade in
+ * battgp_b200/gpytorch/ binds these with ctypes (INTEGRATION.md shows the stub).
+ *
+ * Conventions
+ *   - all matrices are fp64, ROW-MAJOR, leading dimension `ld*` in elements; device pointers come from
+ *     `tensor.data_ptr()`; nothing is allocated behind the caller's back except through `bgp_ctx` (streams,
+ *     events, two small device scalars) -- workspaces are passed in explicitly so torch's caching allocator
+ *     owns all large memory (battgp_full.py:102-120 frees models with empty_cache()).
+ *   - symmetric matrices / Cholesky factors use the LOWER triangle; the strictly upper triangle is never
+ *     read and is left unspecified.
+ *   - `stream` is a cudaStream_t passed as void* (torch.cuda.current_stream().cuda_stream).
+ *   - return value: 0 ok; >0 LAPACK-style 1-based index of the first non-positive pivot; <0 argument or CUDA
+ *     error (BGP_E_*).  No entry point synchronises the device unless stated.
+ *   - no global mutable state; a `bgp_ctx` must not be used from two host threads at once.
+ */
+#ifndef BATTGP_B200_H
+#define BATTGP_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define BGP_VERSION 100
+
+#define BGP_E_ARG   (-1)   /* bad argument (null pointer, negative size, ld too small, misalignment) */
+#define BGP_E_CUDA  (-2)   /* a CUDA runtime call or kernel launch failed; see bgp_last_error()         */
+#define BGP_E_SPEC  (-3)   /* malformed kernel spec                                                    */
+
+/* ---- covariance description ------------------------------------------------------------------------
+ * k(x,x') = sum_i outputscale_i * k_i(x[dims_i], x'[dims_i])  (+ noise on the diagonal of the train block)
+ * replaces: ScaleKernel(WienerKernel[0]) + ScaleKernel(RBFKernel ARD [1,2,3])   cell_gp.py:32-36
+ *           GaussianLikelihood noise                                             cell_gp.py:27
+ *           ScaleKernel(RBFKernel())                                             standard_models.py:24
+ * MATERN52 / PERIODIC: BASELINE.json config 3 (not in the reference; GPyTorch public formulas). */
+enum { BGP_WIENER = 0, BGP_RBF = 1, BGP_MATERN52 = 2, BGP_PERIODIC = 3 };
+#define BGP_MAX_TERMS 4
+#define BGP_MAX_DIMS  8
+
+typedef struct {
+    int32_t type;                       /* BGP_WIENER ...                                         */
+    int32_t ndims;                      /* number of active dims (WIENER: 1)                      */
+    int32_t dims[BGP_MAX_DIMS];         /* column indices into X (GPyTorch active_dims)           */
+    double  outputscale;
+    double  lengthscale[BGP_MAX_DIMS];  /* per active dim (isotropic: repeat)                     */
+    double  period[BGP_MAX_DIMS];       /* PERIODIC only                                          */
+} bgp_term;
+
+typedef struct {
+    int32_t  nterms;
+    int32_t  _pad;
+    bgp_term terms[BGP_MAX_TERMS];
+    double   noise;                     /* sigma_n^2, added where global row == col (train block) */
+} bgp_kernel_spec;
+
+/* number of hyper-parameter gradient slots written by bgp_lml_grad for a spec:
+ * [noise, then per term: outputscale, lengthscale[ndims], (period[ndims] if PERIODIC)] */
+int bgp_grad_slots(const bgp_kernel_spec* spec);
+
+/* ---- context ----------------------------------------------------------------------------------------*/
+typedef struct bgp_ctx bgp_ctx;
+int  bgp_version(void);
+const char* bgp_last_error(void);                         /* thread-local text of the last BGP_E_CUDA */
+int  bgp_ctx_create(int device, bgp_ctx** out);           /* creates the panel (high-priority) stream + events */
+void bgp_ctx_destroy(bgp_ctx* ctx);
+/* tuning knobs: "nb" outer panel width (multiple of 128), "lookahead" 0/1. returns 0 or BGP_E_ARG */
+int  bgp_ctx_set(bgp_ctx* ctx, const char* key, int value);
+/* counts kernels launched through this context since creation (bench.py's gpu_launches) */
+int64_t bgp_ctx_launches(const bgp_ctx* ctx);
+
+/* ---- K1+K2+K3: fused covariance build -------------------------------------------------------------
+ * replaces WienerKernel.forward (wiener_kernel.py:10-32), RBFKernel/ScaleKernel/+ (cell_gp.py:33-36) and the
+ * noise add (cell_gp.py:27) in ONE pass over the output.
+ * X1 [n1,ldx1], X2 [n2,ldx2] row-major device arrays.  out [n1, ldo].
+ *   symmetric != 0 : X2 is ignored (X2 := X1, n2 := n1); only tiles touching the LOWER triangle are written
+ *                    and spec->noise is added on the diagonal.   (train block, ExactGP.__call__)
+ *   symmetric == 0 : full n1 x n2 cross-covariance, no noise.     (kernel.forward(x1, x2): recursive_gp.py:52-57,
+ *                    spatiotemporal_gp.py:157-162, K_*N at predict battcellgp_full.py:173) */
+int bgp_cov_build(bgp_ctx* ctx, const bgp_kernel_spec* spec,
+                  const double* X1, int64_t n1, int64_t ldx1,
+                  const double* X2, int64_t n2, int64_t ldx2,
+                  double* out, int64_t ldo, int symmetric, void* stream);
+
+/* diag k(x,x) (no noise): kernel.forward(x, x, diag=True) / the k_** term of the predictive variance */
+int bgp_cov_diag(bgp_ctx* ctx, const bgp_kernel_spec* spec, const double* X, int64_t n, int64_t ldx,
+                 double* out, void* stream);
+
+/* ---- dense building block (exposed for tests/bench; also the yardstick vs cuBLAS dgemm) ------------
+ * C[M,N] = alpha * A[M,K] * B[N,K]^T + beta * C      (FP64 DMMA tensor pipe)
+ * tri != 0: only elements with (col + coff) <= (row + roff) are computed/stored (lower-triangular SYRK). */
+int bgp_gemm_nt(bgp_ctx* ctx, int64_t M, int64_t N, int64_t K, double alpha,
+                const double* A, int64_t lda, const double* B, int64_t ldb,
+                double beta, double* C, int64_t ldc, int tri, int64_t roff, int64_t coff, void* stream);
+
+/* ---- K4: Cholesky -------------------------------------------------------------------------------------
+ * replaces torch.linalg.cholesky_ex inside GPyTorch's psd_safe_cholesky, reached from ExactGP.__call__
+ * (battcellgp_full.py:173, standard_models.py:41) and ExactMarginalLogLikelihood (training.py:40).
+ * A [n, lda] lower triangle in, L out (in place).  dinv: workspace of bgp_potrf_dinv_elems(n) doubles that
+ * receives the inverses of the 128x128 diagonal blocks of L (needed by the solves below).
+ * Synchronises `stream` at the end (it has to return info).  logdet (host, may be NULL) = 2*sum(log L_ii). */
+int64_t bgp_potrf_dinv_elems(int64_t n);
+int bgp_potrf(bgp_ctx* ctx, double* A, int64_t n, int64_t lda, double* dinv, double* logdet_host, void* stream);
+
+/* ---- K5: alpha = K^-1 y via two triangular sweeps (HBM-bound) -------------------------------------------
+ * replaces cholesky_solve for the mean cache of DefaultPredictionStrategy / inv_quad of the mll.
+ * y [n] in, z = L^-1 y written to z [n] (may be NULL), alpha = L^-T z written to alpha [n]. */
+int bgp_potrs_vec(bgp_ctx* ctx, const double* L, int64_t n, int64_t ldl, const double* dinv,
+                  const double* y, double* z, double* alpha, void* stream);
+
+/* ---- K7: X <- X * L^-T  (X [m, ldx] row-major, m right-hand sides stored as ROWS) -----------------------
+ * replaces solve_triangular / root_inv_decomposition in the predictive covariance (battcellgp_full.py:173-180,
+ * standard_models.py:43-48). */
+int bgp_trsm_rlt(bgp_ctx* ctx, const double* L, int64_t n, int64_t ldl, const double* dinv,
+                 double* X, int64_t m, int64_t ldx, void* stream);
+
+/* ---- K6+K7 fused tail: mean = Kq alpha ; var = kdiag - rowsum(V*V), clamped at min_var --------------------
+ * Kq [m, ldk] = K_*N (before the solve), V [m, ldv] = K_*N L^-T.  mean/var [m].  Either half may be skipped by
+ * passing NULL (Kq,mean) or (V,var).  replaces MultivariateNormal.mean/.variance (battcellgp_full.py:175,180). */
+int bgp_predict_tail(bgp_ctx* ctx, int64_t m, int64_t n, const double* Kq, int64_t ldk, const double* alpha,
+                     const double* V, int64_t ldv, const double* kdiag, double min_var,
+                     double* mean, double* var, void* stream);
+
+/* ---- K8: LML = -0.5 z.z - 0.5 logdet - 0.5 n log(2 pi)  (z = L^-1 y) -------------------------------------
+ * replaces ExactMarginalLogLikelihood.__call__ (training.py:27,40); the facade divides by n.  Synchronises. */
+int bgp_lml(bgp_ctx* ctx, const double* z, int64_t n, double logdet, double* lml_host, void* stream);
+
+/* ---- K9: analytic LML gradient ----------------------------------------------------------------------------
+ * bgp_potri: L (lower, in place) -> K^-1 (lower triangle), via trtri + lauum on the DMMA pipe.
+ * bgp_lml_grad: grad[slot] = 0.5 * sum_ij (alpha_i alpha_j - Kinv_ij) dK_ij/dtheta_slot, recomputing dK tile-wise
+ * from X (no N^2 temporaries).  replaces loss.backward() through cholesky (training.py:41,140).
+ * grad_dev: device array of bgp_grad_slots(spec) doubles (zeroed by the call). */
+int bgp_potri(bgp_ctx* ctx, double* L, int64_t n, int64_t ldl, const double* dinv, double* work, int64_t ldw,
+              void* stream);
+int bgp_lml_grad(bgp_ctx* ctx, const bgp_kernel_spec* spec, const double* X, int64_t n, int64_t ldx,
+                 const double* Kinv, int64_t ldk, const double* alpha, double* grad_dev, void* stream);
+
+/* ---- multi-GPU building blocks (block-row-cyclic sharded Cholesky; the NCCL exchange lives in Python/
+ * torch.distributed, see battgp_b200/sharded.py) --------------------------------------------------------------
+ * factor one nb x nb diagonal block (nb multiple of 128, <= 4096): potrf + all 128-block inverses.  async. */
+int bgp_potrf_block(bgp_ctx* ctx, double* A, int64_t nb, int64_t lda, double* dinv, int32_t* info_dev,
+                    double* logdet_dev, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* BATTGP_B200_H */

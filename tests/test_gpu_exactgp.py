@@ -1,0 +1,101 @@
+"""End-to-end parity of fit + predict (the BASELINE.json configs at oracle-feasible sizes) and size-independent
+properties at larger N."""
+import math
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import gp_oracle as orc
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+def _t(a):
+    return torch.tensor(np.ascontiguousarray(a), dtype=torch.float64, device=DEV)
+
+
+@pytest.mark.parametrize("n", [1000, 4000])
+def test_config1_battgp_fit_predict_matches_oracle(eng, n):
+    """BASELINE config 1 (N=1000, Wiener + RBF-ARD, reference default hyper-parameters) and a 4x larger case.
+    north_star tolerance: predictive mean/var within rtol 1e-4 of the CPU Cholesky path; we assert 1e-7 / 1e-6."""
+    from battgp_b200 import engine as E
+    x, y = orc.synth_field_data(n, seed=0)
+    xq = orc.query_grid(x)
+    f = orc.fit(orc.battgp_spec(), x, y, 2.33e-6)
+    mr, vr = orc.predict(orc.battgp_spec(), x, f, xq)
+    st = E.fit(E.battgp_spec(), _t(x), _t(y), 2.33e-6)
+    m, v = E.predict(st, _t(xq))
+    L = torch.tril(st.L).cpu().numpy()
+    assert np.linalg.norm(L - f.L) / np.linalg.norm(f.L) < 1e-9
+    assert np.linalg.norm(st.alpha.cpu().numpy() - f.alpha) / np.linalg.norm(f.alpha) < 1e-7
+    np.testing.assert_allclose(m.cpu().numpy(), mr, rtol=1e-7)
+    np.testing.assert_allclose(v.cpu().numpy(), vr, rtol=1e-6)
+    assert abs(st.lml - f.lml) < 1e-9 * abs(f.lml)
+    assert st.jitter == 0.0
+
+
+def test_scaled_rbf_full_cov_matches_oracle(eng):
+    from battgp_b200 import engine as E
+    rng = np.random.default_rng(7)
+    x = rng.uniform(-3, 3, size=(50, 3))
+    x[10] = x[3]                                   # duplicates, as test_recursive_gp.py:195-232 does
+    y = np.sin(x.sum(1)) + 0.1 * rng.normal(size=50)
+    xq = rng.uniform(-3, 3, size=(40, 3))
+    f = orc.fit(orc.scaled_rbf_spec(3, 3.0, 2.0), x, y, 0.1)
+    mr, cr = orc.predict(orc.scaled_rbf_spec(3, 3.0, 2.0), x, f, xq, full_cov=True)
+    st = E.fit(E.scaled_rbf_spec(3, 3.0, 2.0), _t(x), _t(y), 0.1)
+    m, c = E.predict(st, _t(xq), full_cov=True)
+    np.testing.assert_allclose(m.cpu().numpy(), mr, rtol=1e-9, atol=1e-12)
+    assert np.linalg.norm(c.cpu().numpy() - cr) / np.linalg.norm(cr) < 1e-9
+
+
+def test_matern_periodic_fit_predict_matches_oracle(eng):
+    from battgp_b200 import engine as E
+    x, y = orc.synth_field_data(1500, seed=3)
+    xq = orc.query_grid(x)
+    spec_o, spec_e = orc.matern_periodic_spec(), E.matern_periodic_spec()
+    f = orc.fit(spec_o, x, y, 2.33e-6)
+    mr, vr = orc.predict(spec_o, x, f, xq)
+    st = E.fit(spec_e, _t(x), _t(y), 2.33e-6)
+    m, v = E.predict(st, _t(xq))
+    np.testing.assert_allclose(m.cpu().numpy(), mr, rtol=1e-7)
+    np.testing.assert_allclose(v.cpu().numpy(), vr, rtol=1e-6)
+    assert abs(st.lml - f.lml) < 1e-9 * abs(f.lml)
+
+
+def test_jitter_retry_and_not_psd(eng):
+    from battgp_b200 import engine as E
+    # exact duplicates with (numerically) zero noise: first attempt fails, jitter 1e-8 rescues it
+    x = np.zeros((40, 3)); x[:, 0] = np.repeat(np.arange(20.0), 2)
+    y = np.arange(40.0)
+    with pytest.warns(E.NumericalWarning):
+        st = E.fit(E.scaled_rbf_spec(3, 1.0, 1.0), _t(x), _t(y), 0.0)
+    assert st.jitter > 0
+    with pytest.raises(E.NotPSDError):
+        E.fit(E.scaled_rbf_spec(3, -1.0, 1.0), _t(x), _t(y), 0.0)     # negative outputscale: never PD
+
+
+def test_large_n_properties(eng):
+    """N = 12288 (beyond what the CI oracle does in seconds): leading-block parity + matrix-free residual
+    (SURVEY.md 8c large-N plan)."""
+    from battgp_b200 import engine as E
+    n, nlead = 12288, 2048
+    x, y = orc.synth_field_data(n, seed=0)
+    xd, yd = _t(x), _t(y)
+    st = E.fit(E.battgp_spec(), xd, yd, 2.33e-6)
+    # (i) L[:k,:k] depends only on K[:k,:k]
+    f = orc.fit(orc.battgp_spec(), x[:nlead], y[:nlead], 2.33e-6)
+    Ll = torch.tril(st.L[:nlead, :nlead]).cpu().numpy()
+    assert np.linalg.norm(Ll - f.L) / np.linalg.norm(f.L) < 1e-9
+    # (ii) || K alpha - y || / || y || with K rebuilt by the fused kernel (full, not just lower)
+    K = eng.cov_build(E.battgp_spec(), xd, xd)
+    r = K @ st.alpha + 2.33e-6 * st.alpha - yd
+    assert (r.norm() / yd.norm()).item() < 1e-8
+    # (iii) variance is within [min_var, prior variance]
+    xq = _t(orc.query_grid(x))
+    m, v = E.predict(st, xq)
+    prior = eng.cov_diag(E.battgp_spec(), xq)
+    assert bool((v >= 1e-10).all()) and bool((v <= prior * (1 + 1e-12)).all())
+    assert bool(torch.isfinite(m).all())

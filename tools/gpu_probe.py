@@ -1,0 +1,103 @@
+"""Development probe (NOT the bench): time the main kernels in isolation on one B200. Prints JSON lines."""
+import json, sys, time
+import torch
+sys.path.insert(0, ".")
+from battgp_b200 import engine as E
+from battgp_b200.synth import synth_field_data, query_grid
+
+dev = torch.device("cuda:0")
+eng = E.get_engine(dev)
+
+def ev(fn, reps=3, warm=1):
+    for _ in range(warm): fn()
+    torch.cuda.synchronize()
+    best = 1e30
+    for _ in range(reps):
+        e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+        e0.record(); fn(); e1.record(); torch.cuda.synchronize()
+        best = min(best, e0.elapsed_time(e1))
+    return best
+
+what = sys.argv[1:] or ["gemm", "potrf", "fit"]
+if "gemm" in what:
+    for (M, N, K) in [(8192, 8192, 8192), (16384, 16384, 1024), (16384, 16384, 512), (16384, 16384, 256), (16384, 16384, 128),
+                      (32768, 1024, 1024), (4096, 4096, 4096), (2048, 2048, 2048), (1024, 1024, 1024), (512, 512, 512), (300, 20000, 20000)]:
+        A = torch.randn(M, K, dtype=torch.float64, device=dev); B = torch.randn(N, K, dtype=torch.float64, device=dev)
+        C = torch.zeros(M, N, dtype=torch.float64, device=dev)
+        ms = ev(lambda: eng.gemm_nt(A, B, C, alpha=-1.0, beta=1.0))
+        ms_cublas = ev(lambda: torch.addmm(C, A, B.t(), beta=1.0, alpha=-1.0, out=C))
+        print(json.dumps({"op": "gemm_nt", "M": M, "N": N, "K": K, "ms": ms, "tflops": 2 * M * N * K / ms * 1e-9,
+                          "cublas_ms": ms_cublas, "cublas_tflops": 2 * M * N * K / ms_cublas * 1e-9}), flush=True)
+        del A, B, C
+    n, k = 16384, 1024
+    A = torch.randn(n, k, dtype=torch.float64, device=dev); C = torch.zeros(n, n, dtype=torch.float64, device=dev)
+    ms = ev(lambda: eng.gemm_nt(A, A, C, alpha=-1.0, beta=1.0, tri=True))
+    print(json.dumps({"op": "syrk_tri", "n": n, "k": k, "ms": ms, "tflops": n * n * k / ms * 1e-9}), flush=True)
+    del A, C
+if "gemmcfg" in what:
+    for cfg in (1, 4, 5, 6):
+        eng.set("gemm_cfg", cfg)
+        for (M, N, K) in [(8192, 8192, 8192), (16384, 16384, 1024), (16384, 16384, 256)]:
+            A = torch.randn(M, K, dtype=torch.float64, device=dev); B = torch.randn(N, K, dtype=torch.float64, device=dev)
+            C = torch.zeros(M, N, dtype=torch.float64, device=dev)
+            ms = ev(lambda: eng.gemm_nt(A, B, C, alpha=-1.0, beta=1.0))
+            print(json.dumps({"op": "gemm_nt", "cfg": cfg, "M": M, "N": N, "K": K, "ms": ms, "tflops": 2 * M * N * K / ms * 1e-9}), flush=True)
+            del A, B, C
+    eng.set("gemm_cfg", 0)
+if "gemmone" in what:
+    M, N, K = 8192, 8192, 2048
+    A = torch.randn(M, K, dtype=torch.float64, device=dev); B = torch.randn(N, K, dtype=torch.float64, device=dev)
+    C = torch.zeros(M, N, dtype=torch.float64, device=dev)
+    for _ in range(3): eng.gemm_nt(A, B, C, alpha=-1.0, beta=1.0)
+    torch.cuda.synchronize()
+if "potrf" in what:
+    for n in (4096, 8192, 16384, 40000):
+        x, y = synth_field_data(n, 0)
+        xd = torch.tensor(x, device=dev); spec = E.battgp_spec()
+        K = E.alloc_matrix(n, n, dev)
+        msb = ev(lambda: eng.cov_build(spec, xd, noise=2.33e-6, symmetric=True, out=K))
+        print(json.dumps({"op": "cov_build_sym", "n": n, "ms": msb, "GBps": 8 * n * (n + 1) / 2 / msb * 1e-6}), flush=True)
+        for nb, la in ((1024, 1), (512, 1), (2048, 1), (1024, 0)):
+            if n < 16384 and nb != 1024: continue
+            eng.set("nb", nb); eng.set("lookahead", la)
+            best = 1e30
+            for r in range(2):
+                eng.cov_build(spec, xd, noise=2.33e-6, symmetric=True, out=K)
+                torch.cuda.synchronize()
+                e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+                e0.record(); info, ld, dinv = eng.potrf(K); e1.record(); torch.cuda.synchronize()
+                best = min(best, e0.elapsed_time(e1))
+            print(json.dumps({"op": "potrf", "n": n, "nb": nb, "lookahead": la, "info": info, "ms": best,
+                              "tflops": n ** 3 / 3 / best * 1e-9}), flush=True)
+        eng.set("nb", 1024); eng.set("lookahead", 1)
+        if n <= 16384:
+            eng.cov_build(spec, xd, noise=2.33e-6, symmetric=True, out=K)
+            Kc = K.clone()
+            ms = ev(lambda: torch.linalg.cholesky_ex(Kc.copy_(K)), reps=2)
+            print(json.dumps({"op": "torch_cholesky_ex(+copy)", "n": n, "ms": ms}), flush=True)
+            del Kc
+        del K
+        torch.cuda.empty_cache()
+if "fit" in what:
+    for n in (8192, 40000):
+        x, y = synth_field_data(n, 0)
+        xd, yd = torch.tensor(x, device=dev), torch.tensor(y, device=dev)
+        xq = torch.tensor(query_grid(x), device=dev)
+        K = E.alloc_matrix(n, n, dev)
+        for r in range(2):
+            torch.cuda.synchronize(); t0 = time.perf_counter()
+            st = E.fit(E.battgp_spec(), xd, yd, 2.33e-6, K_out=K)
+            torch.cuda.synchronize(); t1 = time.perf_counter()
+            m, v = E.predict(st, xq)
+            torch.cuda.synchronize(); t2 = time.perf_counter()
+        # phase split
+        t = {}
+        t["build"] = ev(lambda: eng.cov_build(st.spec, xd, noise=2.33e-6, symmetric=True, out=K), reps=2)
+        info, ld, dinv = eng.potrf(K)
+        t["potrs_vec"] = ev(lambda: eng.potrs_vec(K, dinv, yd), reps=2)
+        Kq = eng.cov_build(st.spec, xq, xd)
+        t["trsm300"] = ev(lambda: eng.trsm_rlt(K, dinv, Kq), reps=2)
+        print(json.dumps({"op": "fit+predict", "n": n, "fit_s": t1 - t0, "predict_s": t2 - t1, "lml": st.lml,
+                          "mean0": float(m[0]), "var0": float(v[0]), "phases_ms": t, "launches": eng.launches}), flush=True)
+        del K, st
+        torch.cuda.empty_cache()
