@@ -64,11 +64,38 @@ gemm_nt_kernel(GemmArgs g, int tiles_m, int tiles_n, int c_vec) {
     const double* __restrict__ B = g.B;
     const int64_t lda = g.lda, ldb = g.ldb;
 
+    // Per-thread copy slots: slot i of a thread always covers the same (row, 16-byte column) of the A / B tile, so
+    // the source pointers and row predicates are computed once; a full chunk is then ASLOTS+BSLOTS branch-free
+    // cp.async per thread (zero-fill for rows outside the matrix), only the ragged last K chunk takes the slow path.
+    constexpr int RSTEP = NT / SEG;
+    constexpr int ASLOTS = BM * SEG / NT, BSLOTS = BN * SEG / NT;
+    static_assert(NT % SEG == 0 && (BM * SEG) % NT == 0 && (BN * SEG) % NT == 0, "tile/thread mismatch");
+    const int lr = tid / SEG, lc = (tid % SEG) * 2;
+    const double* a_base = A + (int64_t)(m0 + lr) * lda + lc;
+    const double* b_base = B + (int64_t)(n0 + lr) * ldb + lc;
+    const int64_t a_rstep = (int64_t)RSTEP * lda, b_rstep = (int64_t)RSTEP * ldb;
+    unsigned a_mask = 0, b_mask = 0;
+#pragma unroll
+    for (int i = 0; i < ASLOTS; i++) a_mask |= (m0 + lr + i * RSTEP < M) ? (1u << i) : 0u;
+#pragma unroll
+    for (int i = 0; i < BSLOTS; i++) b_mask |= (n0 + lr + i * RSTEP < N) ? (1u << i) : 0u;
+    const int sm_off = lr * PITCH + lc;
+
     auto load_chunk = [&](int stage, int k0) {
         double* as = As + (size_t)stage * BM * PITCH;
         double* bs = Bs + (size_t)stage * BN * PITCH;
-        if (ALIGNED) {
+        if (ALIGNED && k0 + BK <= K) {
 #pragma unroll
+            for (int i = 0; i < ASLOTS; i++) {
+                const bool ok = (a_mask >> i) & 1u;
+                cp_async16(as + sm_off + i * RSTEP * PITCH, ok ? a_base + i * a_rstep + k0 : A, ok ? 16 : 0);
+            }
+#pragma unroll
+            for (int i = 0; i < BSLOTS; i++) {
+                const bool ok = (b_mask >> i) & 1u;
+                cp_async16(bs + sm_off + i * RSTEP * PITCH, ok ? b_base + i * b_rstep + k0 : B, ok ? 16 : 0);
+            }
+        } else if (ALIGNED) {
             for (int s = tid; s < BM * SEG; s += NT) {
                 const int r = s / SEG, c = (s % SEG) * 2;
                 const int gr = m0 + r, gk = k0 + c;
@@ -77,7 +104,6 @@ gemm_nt_kernel(GemmArgs g, int tiles_m, int tiles_n, int c_vec) {
                 const double* src = bytes ? A + (int64_t)gr * lda + gk : A;
                 cp_async16(as + r * PITCH + c, src, bytes);
             }
-#pragma unroll
             for (int s = tid; s < BN * SEG; s += NT) {
                 const int r = s / SEG, c = (s % SEG) * 2;
                 const int gr = n0 + r, gk = k0 + c;
@@ -206,21 +232,24 @@ static int launch_cfg(Ctx* ctx, const GemmArgs& g, cudaStream_t st) {
     return 0;
 }
 
-// cfg: 0 auto, 1 = 128x128, 2 = 64x128 (in-place safe for N<=128, more CTAs for short M), 3 = 64x64;
+// cfg: 0 auto, 1 = 128x128, 2 = 64x128 (in-place safe for N<=128, short M), 3 = 64x64, 5 = 128x64 (default big);
 // 4..7 are experimental variants selectable through bgp_ctx_set("gemm_cfg", k)
 int gemm_nt_cfg(Ctx* ctx, const GemmArgs& g, int cfg, cudaStream_t st) {
     if (g.M <= 0 || g.N <= 0) return 0;
     if (cfg == 0) {
-        const int64_t t128 = (int64_t)((g.M + 127) / 128) * ((g.N + 127) / 128);
-        cfg = (t128 >= 120) ? (ctx->gemm_cfg ? ctx->gemm_cfg : 1) : 3;
+        // 128x64 tiles, 2 CTAs/SM (16 warps/SM hide each other's barriers): 33.9 TF/s at 8192^3 vs 29.8 for 128x128
+        const int64_t t = (int64_t)((g.M + 127) / 128) * ((g.N + 63) / 64);
+        cfg = (t >= 240) ? (ctx->gemm_cfg ? ctx->gemm_cfg : 5) : 3;
+        // short-and-wide products (the M = 300 query block of the predictive variance): 64-row tiles waste less
+        if (g.M <= 1024 && (((g.M + 127) / 128) * 128 - g.M) >= 64 && (int64_t)((g.M + 63) / 64) * ((g.N + 127) / 128) >= 240)
+            cfg = 2;
     }
     switch (cfg) {
         case 1: return launch_cfg<128, 128, 64, 32, 16, 4, 1>(ctx, g, st);
-        case 2: return launch_cfg<64, 128, 32, 64, 16, 4, 1>(ctx, g, st);
+        case 2: return launch_cfg<64, 128, 32, 32, 16, 3, 2>(ctx, g, st);    // 8 warps, 2 CTAs / SM
         case 4: return launch_cfg<128, 128, 32, 32, 16, 4, 1>(ctx, g, st);   // 16 warps
         case 5: return launch_cfg<128, 64, 32, 32, 16, 3, 2>(ctx, g, st);    // 2 CTAs / SM
         case 6: return launch_cfg<128, 128, 64, 32, 32, 3, 1>(ctx, g, st);   // BK = 32
-        case 7: return launch_cfg<256, 128, 64, 64, 16, 3, 1>(ctx, g, st);   // 256x128, 8 warps of 64x64
         default: return launch_cfg<64, 64, 32, 32, 16, 4, 1>(ctx, g, st);
     }
 }

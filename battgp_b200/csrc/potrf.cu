@@ -14,91 +14,186 @@
 
 namespace bgp {
 
-constexpr int LP = LEAF + 1;   // shared-memory pitch (doubles) of the leaf block
+constexpr int SP = LEAF + 4;    // shared-memory pitch of the leaf block: == 4 (mod 16) -> conflict-free DMMA fragment loads
+constexpr int BP = 36;          // pitch of the 32-wide scratch blocks (== 4 mod 16)
 
-// One CTA: S = lower(A[0:n,0:n]); S <- chol(S); A <- S; dinv <- inv(S) (dense 128x128, zeros above diag,
-// identity padding when n < 128).  info: atomicMin of the 1-based global index of the first bad pivot.
+__device__ __forceinline__ void dmma_leaf(double& c0, double& c1, double a, double b) {
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+                 : "+d"(c0), "+d"(c1)
+                 : "d"(a), "d"(b));
+}
+__device__ __forceinline__ double shfl_d(double v, int src) { return __shfl_sync(0xffffffffu, v, src); }
+
+// One warp, lane i = row i of the 32x32 diagonal block at D (pitch SP).  In-place lower Cholesky held in registers
+// (column broadcasts by shuffle), then the inverse of the factor, one column per lane, into X (pitch BP, zeros above
+// the diagonal).  Returns sum(log d_j); *bad = first failing local column + 1 (0 = none).
+__device__ __forceinline__ double warp_potrf32_inv(double* D, double* X, int lane, int* bad) {
+    double a[32];
+#pragma unroll
+    for (int k = 0; k < 32; k++) a[k] = (k <= lane) ? D[lane * SP + k] : 0.0;
+    double logsum = 0.0, my_rdiag = 1.0;
+    int fail = 0;
+#pragma unroll
+    for (int j = 0; j < 32; j++) {
+        const double d = shfl_d(a[j], j);
+        if (!(d > 0.0) && fail == 0) fail = j + 1;
+        logsum += log(d);
+        const double r = sqrt(d), rinv = 1.0 / r;
+        const double l = (lane == j) ? r : a[j] * rinv;
+        a[j] = l;
+        if (lane == j) my_rdiag = rinv;
+#pragma unroll
+        for (int k = j + 1; k < 32; k++) a[k] = fma(-l, shfl_d(l, k), a[k]);
+    }
+    *bad = fail;
+#pragma unroll
+    for (int k = 0; k < 32; k++) D[lane * SP + k] = (k <= lane) ? a[k] : 0.0;
+    __syncwarp();
+    // inverse: lane c owns column c;  x_i = (delta_ic - sum_{k<i} L_ik x_k) / L_ii   (x_k = 0 for k < c falls out)
+    double x[32];
+#pragma unroll
+    for (int i = 0; i < 32; i++) {
+        double s0 = (i == lane) ? 1.0 : 0.0, s1 = 0.0;
+#pragma unroll
+        for (int k = 0; k < i; k += 2) {
+            s0 = fma(-D[i * SP + k], x[k], s0);
+            if (k + 1 < i) s1 = fma(-D[i * SP + k + 1], x[k + 1], s1);
+        }
+        x[i] = (s0 + s1) * shfl_d(my_rdiag, i);
+    }
+#pragma unroll
+    for (int i = 0; i < 32; i++) X[i * BP + lane] = (i >= lane) ? x[i] : 0.0;
+    return logsum;
+}
+
+// One CTA (8 warps): S = lower(A[0:n,0:n]) (identity-padded to 128); S <- chol(S) by 32-wide panels -- diagonal block
+// factored + inverted by one warp in registers, panel solve and trailing update as in-smem DMMA products; A <- L;
+// then L^-1 by block columns (again DMMA products) -> dinv (dense 128x128, zeros above the diagonal).
+// info: atomicMin of the 1-based global index of the first non-positive pivot.  logdet += sum log d_j = log|A|.
 __global__ void __launch_bounds__(256)
 leaf_potrf_trtri_kernel(double* A, int64_t lda, int n, double* dinv, int32_t* info, int64_t gofs, double* logdet) {
-    extern __shared__ double S[];          // [LEAF][LP]; strictly-upper part later holds inv(L)^T
-    __shared__ double s_dinv[LEAF];        // 1 / L_ii
-    const int tid = threadIdx.x;
+    extern __shared__ double sm[];
+    double* S = sm;                          // [128][SP]
+    double* T = S + LEAF * SP;               // [96][BP]   scratch for the inverse phase
+    double* Dg = T + 96 * BP;                // [4][32][BP] inverses of the diagonal 32-blocks
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int fr = lane >> 2, fk = lane & 3;
 
     for (int idx = tid; idx < LEAF * LEAF; idx += 256) {
         const int i = idx >> 7, j = idx & (LEAF - 1);
         double v = 0.0;
         if (i < n) { if (j <= i) v = A[(int64_t)i * lda + j]; }
         else if (i == j) v = 1.0;
-        S[i * LP + j] = v;
-    }
-
-    // right-looking, one barrier per column: iteration j first finishes (scales) column j-1, then applies the
-    // rank-1 update of the still unscaled column j:  S[i][k] -= S[i][j] S[k][j] / d_j
-    const int tx = tid & 31, ty = tid >> 5;
-    double d_prev = 1.0;
-    double logsum = 0.0;
-    bool failed = false;
-    for (int j = 0; j <= n; j++) {
-        __syncthreads();
-        if (j > 0) {
-            const double r = sqrt(d_prev), rinv = 1.0 / r;
-            for (int i = j - 1 + tid; i < n; i += 256) S[i * LP + (j - 1)] = (i == j - 1) ? r : S[i * LP + (j - 1)] * rinv;
-        }
-        if (j == n) break;
-        const double d = S[j * LP + j];
-        if (!(d > 0.0) && !failed) {      // also catches NaN
-            failed = true;
-            if (tid == 0) atomicMin(info, (int32_t)min((int64_t)INT_MAX, gofs + j + 1));
-        }
-        logsum += log(d);
-        const double dinv_j = 1.0 / d;
-        for (int i = j + 1 + ty; i < n; i += 8) {
-            const double lij = S[i * LP + j] * dinv_j;
-            for (int k = j + 1 + tx; k <= i; k += 32) S[i * LP + k] -= lij * S[k * LP + j];
-        }
-        d_prev = d;
+        S[i * SP + j] = v;
     }
     __syncthreads();
-    if (tid == 0 && logdet != nullptr) atomicAdd(logdet, logsum);   // sum log d_j = 2 sum log L_jj
+
+    double logsum = 0.0;
+    for (int kb = 0; kb < 4; kb++) {
+        const int c0 = kb * 32, r0 = c0 + 32, mt = (LEAF - r0) / 8;     // mt row tiles below the diagonal block
+        if (warp == 0) {
+            int bad;
+            logsum += warp_potrf32_inv(S + c0 * SP + c0, Dg + kb * 32 * BP, lane, &bad);
+            if (bad && lane == 0) atomicMin(info, (int32_t)min((int64_t)INT_MAX, gofs + c0 + bad));
+        }
+        __syncthreads();
+        // panel solve  P <- P * inv(Ld)^T   (rows r0.., columns c0..c0+31); one warp owns whole row tiles (in place)
+        for (int ti = warp; ti < mt; ti += 8) {
+            double acc[4][2];
+#pragma unroll
+            for (int t = 0; t < 4; t++) acc[t][0] = acc[t][1] = 0.0;
+            const double* ap = S + (r0 + ti * 8 + fr) * SP + c0 + fk;
+            const double* bp = Dg + kb * 32 * BP + fr * BP + fk;
+#pragma unroll
+            for (int k4 = 0; k4 < 32; k4 += 4) {
+                const double av = ap[k4];
+#pragma unroll
+                for (int t = 0; t < 4; t++) dmma_leaf(acc[t][0], acc[t][1], av, bp[t * 8 * BP + k4]);
+            }
+            __syncwarp();
+            double* cp = S + (r0 + ti * 8 + fr) * SP + c0 + 2 * fk;
+#pragma unroll
+            for (int t = 0; t < 4; t++) { cp[t * 8] = acc[t][0]; cp[t * 8 + 1] = acc[t][1]; }
+        }
+        __syncthreads();
+        // trailing update  S[i][j] -= sum_k P[i][k] P[j][k]  over lower 8x8 tiles of the remaining block
+        int cnt = 0;
+        for (int ti = 0; ti < mt; ti++) {
+            for (int tj = 0; tj <= ti; tj++, cnt++) {
+                if ((cnt & 7) != warp) continue;
+                const double* ap = S + (r0 + ti * 8 + fr) * SP + c0 + fk;
+                const double* bp = S + (r0 + tj * 8 + fr) * SP + c0 + fk;
+                double* cp = S + (r0 + ti * 8 + fr) * SP + r0 + tj * 8 + 2 * fk;
+                double n0 = 0.0, n1 = 0.0;
+#pragma unroll
+                for (int k4 = 0; k4 < 32; k4 += 4) dmma_leaf(n0, n1, ap[k4], bp[k4]);
+                cp[0] -= n0;
+                cp[1] -= n1;
+            }
+        }
+        __syncthreads();
+    }
+    if (tid == 0 && logdet != nullptr) atomicAdd(logdet, logsum);
 
     // write L back (lower triangle only)
     for (int idx = tid; idx < n * LEAF; idx += 256) {
         const int i = idx >> 7, j = idx & (LEAF - 1);
-        if (j <= i) A[(int64_t)i * lda + j] = S[i * LP + j];
+        if (j <= i) A[(int64_t)i * lda + j] = S[i * SP + j];
     }
-    if (tid < LEAF) s_dinv[tid] = 1.0 / S[tid * LP + tid];
     __syncthreads();
-
-    // inverse by forward substitution, one column per thread pair (k split by parity):
-    //   X[j][j] = 1/L[j][j];  X[i][j] = -(sum_{k=j}^{i-1} L[i][k] X[k][j]) / L[i][i]
-    // X[i][j] (i > j) is kept transposed in the unused strictly-upper triangle: S[j][i].
-    {
-        const int j = tid >> 1, par = tid & 1;
-        const int jw = (tid >> 5) * 16;            // first column handled by this warp (warp-uniform loop bounds)
-        for (int i = jw + 1; i < LEAF; i++) {
-            double s = 0.0;
-            if (i > j) {
-                // k = j term uses X[j][j] = s_dinv[j]
-                if (par == 0) s = S[i * LP + j] * s_dinv[j];
-                for (int k = j + 1 + par; k < i; k += 2) s = fma(S[i * LP + k], S[j * LP + k], s);
+    // ---- inverse: X = L^-1 in place.  Diagonal 32-blocks come from Dg; block column j (2,1,0):
+    //      X[r0:, j] = -X_trail * L[r0:, j] * X_jj   with X_trail = inv(L[r0:, r0:]) already in place
+    for (int idx = tid; idx < 4 * 32 * 32; idx += 256) {
+        const int b = idx >> 10, i = (idx >> 5) & 31, j = idx & 31;
+        S[(b * 32 + i) * SP + b * 32 + j] = Dg[b * 32 * BP + i * BP + j];
+    }
+    __syncthreads();
+    for (int jb = 2; jb >= 0; jb--) {
+        const int cb = jb * 32, r0 = cb + 32, mt = (LEAF - r0) / 8;
+        // (i) T = X_trail * B   (NN; X_trail lower-triangular: k < (ti+1)*8)
+        for (int ti = warp; ti < mt; ti += 8) {
+            double acc[4][2];
+#pragma unroll
+            for (int t = 0; t < 4; t++) acc[t][0] = acc[t][1] = 0.0;
+            const double* ap = S + (r0 + ti * 8 + fr) * SP + r0 + fk;
+            const double* bp = S + (r0 + fk) * SP + cb + fr;
+            for (int k4 = 0; k4 < (ti + 1) * 8; k4 += 4) {
+                const double av = ap[k4];
+#pragma unroll
+                for (int t = 0; t < 4; t++) dmma_leaf(acc[t][0], acc[t][1], av, bp[k4 * SP + t * 8]);
             }
-            s += __shfl_xor_sync(0xffffffffu, s, 1);
-            if (i > j && par == 0) S[j * LP + i] = -s * s_dinv[i];
-            __syncwarp();
+            double* cp = T + (ti * 8 + fr) * BP + 2 * fk;
+#pragma unroll
+            for (int t = 0; t < 4; t++) { cp[t * 8] = acc[t][0]; cp[t * 8 + 1] = acc[t][1]; }
         }
+        __syncthreads();
+        // (ii) B <- -T * X_jj   (NN; X_jj = Dg[jb], explicit zeros above its diagonal)
+        for (int ti = warp; ti < mt; ti += 8) {
+            double acc[4][2];
+#pragma unroll
+            for (int t = 0; t < 4; t++) acc[t][0] = acc[t][1] = 0.0;
+            const double* ap = T + (ti * 8 + fr) * BP + fk;
+            const double* bp = Dg + jb * 32 * BP + fk * BP + fr;
+#pragma unroll
+            for (int k4 = 0; k4 < 32; k4 += 4) {
+                const double av = ap[k4];
+#pragma unroll
+                for (int t = 0; t < 4; t++) dmma_leaf(acc[t][0], acc[t][1], av, bp[k4 * BP + t * 8]);
+            }
+            double* cp = S + (r0 + ti * 8 + fr) * SP + cb + 2 * fk;
+#pragma unroll
+            for (int t = 0; t < 4; t++) { cp[t * 8] = -acc[t][0]; cp[t * 8 + 1] = -acc[t][1]; }
+        }
+        __syncthreads();
     }
-    __syncthreads();
     for (int idx = tid; idx < LEAF * LEAF; idx += 256) {
         const int i = idx >> 7, j = idx & (LEAF - 1);
-        double v = 0.0;
-        if (j < i) v = S[j * LP + i];
-        else if (j == i) v = s_dinv[i];
-        dinv[idx] = v;
+        dinv[idx] = (j <= i) ? S[i * SP + j] : 0.0;
     }
 }
 
 static int launch_leaf(Ctx* ctx, double* A, int64_t lda, int n, double* dinv, int64_t gofs, cudaStream_t st) {
-    constexpr int SMEM = LEAF * LP * sizeof(double);
+    constexpr int SMEM = (LEAF * SP + 96 * BP + 4 * 32 * BP) * sizeof(double);
     static thread_local uint64_t attr_done = 0;
     const uint64_t bit = 1ull << (ctx->device & 63);
     if (!(attr_done & bit)) {
@@ -125,7 +220,7 @@ int trsm_rlt_rec(Ctx* ctx, const double* L, int64_t n, int64_t ldl, const double
     if (n <= LEAF) {
         // in place: C aliases A; safe because one CTA owns all n <= 128 columns of its rows
         GemmArgs g{X, ldx, dinv, LEAF, X, ldx, (int)m, (int)n, (int)n, 1.0, 0.0, 0, 0, 0};
-        return gemm_nt_cfg(ctx, g, m >= 148 * 128 ? 1 : 2, st);
+        return gemm_nt_cfg(ctx, g, m >= 148 * 2 * 128 ? 1 : 2, st);
     }
     const int64_t n1 = split_point(n), n2 = n - n1;
     int rc = trsm_rlt_rec(ctx, L, n1, ldl, dinv, X, m, ldx, st);

@@ -32,6 +32,23 @@ __global__ void __launch_bounds__(256) trsv_first_kernel(const double* __restric
 
 // forward step for block k (rows k0..k0+nbk-1 solved, x holds x_k at x[k0..]):
 //   rows i >= k0+nbk:  b[i] -= L[i, k0:k0+nbk] . x_k ;  CTA 0 then x[k0+nbk ..] = Dinv_{k+1} * b[k0+nbk ..]
+// Each warp owns 16 rows and issues all 64 loads of its 16x128 slab before reducing (the sweep is pure latency).
+__device__ __forceinline__ void rows16_dot(const double* __restrict__ base, int64_t ld, int nrows, int ncols, int lane,
+                                           double x0, double x1, double x2, double x3, double (&out)[16]) {
+    double a[16][4];
+#pragma unroll
+    for (int u = 0; u < 16; u++) {
+        const double* lp = base + (int64_t)u * ld;
+        const bool rok = u < nrows;
+        a[u][0] = (rok && lane < ncols) ? lp[lane] : 0.0;
+        a[u][1] = (rok && lane + 32 < ncols) ? lp[lane + 32] : 0.0;
+        a[u][2] = (rok && lane + 64 < ncols) ? lp[lane + 64] : 0.0;
+        a[u][3] = (rok && lane + 96 < ncols) ? lp[lane + 96] : 0.0;
+    }
+#pragma unroll
+    for (int u = 0; u < 16; u++) out[u] = warp_sum(a[u][0] * x0 + a[u][1] * x1 + a[u][2] * x2 + a[u][3] * x3);
+}
+
 __global__ void __launch_bounds__(256)
 trsv_fwd_step_kernel(const double* __restrict__ L, int64_t ldl, int64_t n, int64_t k0, int nbk,
                      const double* __restrict__ dinv_next, double* b, double* x) {
@@ -41,42 +58,33 @@ trsv_fwd_step_kernel(const double* __restrict__ L, int64_t ldl, int64_t n, int64
     if (tid < LEAF) sx[tid] = tid < nbk ? x[k0 + tid] : 0.0;
     __syncthreads();
     const int64_t r0 = k0 + nbk + (int64_t)blockIdx.x * LEAF;
-    const double x0 = sx[lane], x1 = sx[lane + 32], x2 = sx[lane + 64], x3 = sx[lane + 96];
-    // 16 rows per warp, 4 at a time for memory-level parallelism
-    for (int rr = 0; rr < 16; rr += 4) {
-        double s[4];
+    const int64_t wr0 = r0 + warp * 16;
+    const int nrows = (int)max((int64_t)0, min((int64_t)16, n - wr0));
+    double s[16];
+    rows16_dot(L + wr0 * ldl + k0, ldl, nrows, nbk, lane, sx[lane], sx[lane + 32], sx[lane + 64], sx[lane + 96], s);
+    // lane u finishes row u of this warp
+    double mine = 0.0;
 #pragma unroll
-        for (int u = 0; u < 4; u++) {
-            const int64_t row = r0 + warp * 16 + rr + u;
-            s[u] = 0.0;
-            if (row < n) {
-                const double* lp = L + row * ldl + k0;
-                double a0 = lane < nbk ? lp[lane] : 0.0;
-                double a1 = lane + 32 < nbk ? lp[lane + 32] : 0.0;
-                double a2 = lane + 64 < nbk ? lp[lane + 64] : 0.0;
-                double a3 = lane + 96 < nbk ? lp[lane + 96] : 0.0;
-                s[u] = a0 * x0 + a1 * x1 + a2 * x2 + a3 * x3;
-            }
-        }
-#pragma unroll
-        for (int u = 0; u < 4; u++) {
-            const int64_t row = r0 + warp * 16 + rr + u;
-            const double t = warp_sum(s[u]);
-            if (row < n) {
-                const double nb_ = b[row] - t;
-                if (lane == 0) b[row] = nb_;
-                if (blockIdx.x == 0) sb[warp * 16 + rr + u] = nb_;
-            }
-        }
+    for (int u = 0; u < 16; u++) if (lane == u) mine = s[u];
+    if (lane < nrows) {
+        const double nb_ = b[wr0 + lane] - mine;
+        b[wr0 + lane] = nb_;
+        if (blockIdx.x == 0) sb[warp * 16 + lane] = nb_;
     }
     if (blockIdx.x != 0) return;
     __syncthreads();
     const int nnext = (int)min((int64_t)LEAF, n - r0);
-    for (int r = warp; r < nnext; r += 8) {
-        double s = 0.0;
-        for (int c = lane; c <= r; c += 32) s = fma(dinv_next[r * LEAF + c], sb[c], s);
-        s = warp_sum(s);
-        if (lane == 0) x[r0 + r] = s;
+    if (lane >= 0) {     // x_{k+1} = Dinv_{k+1} * b_{k+1}: again 16 rows per warp
+        const int rr0 = warp * 16;
+        const int nr = max(0, min(16, nnext - rr0));
+        double t[16];
+        rows16_dot(dinv_next + rr0 * LEAF, LEAF, nr, nnext, lane, lane < nnext ? sb[lane] : 0.0,
+                   lane + 32 < nnext ? sb[lane + 32] : 0.0, lane + 64 < nnext ? sb[lane + 64] : 0.0,
+                   lane + 96 < nnext ? sb[lane + 96] : 0.0, t);
+        double m2 = 0.0;
+#pragma unroll
+        for (int u = 0; u < 16; u++) if (lane == u) m2 = t[u];
+        if (lane < nr) x[r0 + rr0 + lane] = m2;
     }
 }
 
@@ -96,41 +104,50 @@ __global__ void __launch_bounds__(128) trsv_last_kernel(const double* __restrict
 
 // backward step for block k (x_k at x[k0..k0+nbk-1] solved): columns c < k0:  b[c] -= sum_r L[k0+r][c] x_k[r];
 // CTA 0 owns the 128 columns just left of k0 and then applies inv(L_{k-1,k-1})^T.
-// 256 threads = 128 columns x 2 row-halves.
-__global__ void __launch_bounds__(256)
+// 512 threads = 128 columns x 4 row-quarters (32 independent loads per thread, all issued up front).
+__global__ void __launch_bounds__(512)
 trsv_bwd_step_kernel(const double* __restrict__ L, int64_t ldl, int64_t k0, int nbk,
                      const double* __restrict__ dinv_prev, double* b, double* x) {
     __shared__ double sx[LEAF];
-    __shared__ double part[LEAF];
+    __shared__ double part[4][LEAF];
     __shared__ double sb[LEAF];
     const int tid = threadIdx.x;
     if (tid < LEAF) sx[tid] = tid < nbk ? x[k0 + tid] : 0.0;
     __syncthreads();
-    const int cl = tid & (LEAF - 1), half = tid >> 7;
-    const int64_t c = k0 - LEAF - (int64_t)blockIdx.x * LEAF + cl;   // CTA 0: columns k0-128 .. k0-1
-    double s = 0.0;
-    if (c >= 0) {
-        const double* lp = L + (k0 + half * 64) * ldl + c;
-        const int rend = min(64, nbk - half * 64);
-#pragma unroll 8
-        for (int r = 0; r < rend; r++) s = fma(lp[(int64_t)r * ldl], sx[half * 64 + r], s);
+    const int cl = tid & (LEAF - 1), q = tid >> 7;
+    const int64_t c = k0 - LEAF - (int64_t)blockIdx.x * LEAF + cl;   // CTA 0: columns k0-128 .. k0-1 (always >= 0)
+    {
+        const double* lp = L + (k0 + q * 32) * ldl + c;
+        double v[32];
+#pragma unroll
+        for (int r = 0; r < 32; r++) v[r] = (q * 32 + r < nbk) ? lp[(int64_t)r * ldl] : 0.0;
+        double s0 = 0.0, s1 = 0.0;
+#pragma unroll
+        for (int r = 0; r < 32; r += 2) { s0 = fma(v[r], sx[q * 32 + r], s0); s1 = fma(v[r + 1], sx[q * 32 + r + 1], s1); }
+        part[q][cl] = s0 + s1;
     }
-    if (half == 1) part[cl] = s;
     __syncthreads();
     double nbv = 0.0;
-    if (half == 0 && c >= 0) {
-        nbv = b[c] - (s + part[cl]);
+    if (q == 0) {
+        nbv = b[c] - ((part[0][cl] + part[1][cl]) + (part[2][cl] + part[3][cl]));
         b[c] = nbv;
     }
     if (blockIdx.x != 0) return;
-    if (half == 0) sb[cl] = nbv;
+    if (q == 0) sb[cl] = nbv;
     __syncthreads();
-    // x_{k-1}[i] = sum_{r >= i} DinvPrev[r][i] * b_{k-1}[r]   (block k-1 is always a full 128 block)
-    if (tid < LEAF) {
-        double t = 0.0;
-        for (int r = tid; r < LEAF; r++) t = fma(dinv_prev[r * LEAF + tid], sb[r], t);
-        x[k0 - LEAF + tid] = t;
+    // x_{k-1}[i] = sum_{r >= i} DinvPrev[r][i] * b_{k-1}[r]   (block k-1 is always a full 128 block; zeros above diag)
+    {
+        const double* dp = dinv_prev + (q * 32) * LEAF + cl;
+        double v[32];
+#pragma unroll
+        for (int r = 0; r < 32; r++) v[r] = dp[r * LEAF];
+        double s0 = 0.0, s1 = 0.0;
+#pragma unroll
+        for (int r = 0; r < 32; r += 2) { s0 = fma(v[r], sb[q * 32 + r], s0); s1 = fma(v[r + 1], sb[q * 32 + r + 1], s1); }
+        part[q][cl] = s0 + s1;
     }
+    __syncthreads();
+    if (q == 0) x[k0 - LEAF + cl] = (part[0][cl] + part[1][cl]) + (part[2][cl] + part[3][cl]);
 }
 
 int trsv_lower(Ctx* ctx, const double* L, int64_t n, int64_t ldl, const double* dinv, double* b, double* x,
@@ -161,7 +178,7 @@ int trsv_lower_t(Ctx* ctx, const double* L, int64_t n, int64_t ldl, const double
         const int64_t k0 = k * LEAF;
         const int nbk = (int)min((int64_t)LEAF, n - k0);
         const unsigned grid = (unsigned)(k0 / LEAF);
-        trsv_bwd_step_kernel<<<grid, 256, 0, st>>>(L, ldl, k0, nbk, dinv + (k - 1) * (int64_t)LEAF * LEAF, b, x);
+        trsv_bwd_step_kernel<<<grid, 512, 0, st>>>(L, ldl, k0, nbk, dinv + (k - 1) * (int64_t)LEAF * LEAF, b, x);
         BGP_LAUNCH_OK(ctx);
     }
     return 0;

@@ -298,7 +298,7 @@ class FitState:
 
 
 def fit(spec: KernelSpec, x: torch.Tensor, y: torch.Tensor, noise: float, *, K_out: Optional[torch.Tensor] = None,
-        kbuilder=None) -> FitState:
+        kbuilder=None, potrf_events=None) -> FitState:
     """build K -> Cholesky (with GPyTorch's jitter retries) -> alpha -> LML.  ``kbuilder(out, extra_noise)`` may
     replace the fused build for kernels the engine does not know (it must fill the lower triangle of ``out``)."""
     eng = get_engine(x.device)
@@ -310,7 +310,11 @@ def fit(spec: KernelSpec, x: torch.Tensor, y: torch.Tensor, noise: float, *, K_o
             eng.cov_build(spec, x, noise=noise + jitter, symmetric=True, out=K)
         else:
             kbuilder(K, noise + jitter)
+        if potrf_events is not None:
+            potrf_events[0].record()
         info, logdet, dinv = eng.potrf(K)
+        if potrf_events is not None:
+            potrf_events[1].record()
         if info == 0 and math.isfinite(logdet):
             break
         if info == 0 and not math.isfinite(logdet):

@@ -51,13 +51,13 @@ if "gemmone" in what:
     for _ in range(3): eng.gemm_nt(A, B, C, alpha=-1.0, beta=1.0)
     torch.cuda.synchronize()
 if "potrf" in what:
-    for n in (4096, 8192, 16384, 40000):
+    for n in ((40000,) if 'only40k' in what else (4096, 8192, 16384, 40000)):
         x, y = synth_field_data(n, 0)
         xd = torch.tensor(x, device=dev); spec = E.battgp_spec()
         K = E.alloc_matrix(n, n, dev)
         msb = ev(lambda: eng.cov_build(spec, xd, noise=2.33e-6, symmetric=True, out=K))
         print(json.dumps({"op": "cov_build_sym", "n": n, "ms": msb, "GBps": 8 * n * (n + 1) / 2 / msb * 1e-6}), flush=True)
-        for nb, la in ((1024, 1), (512, 1), (2048, 1), (1024, 0)):
+        for nb, la in ((1024, 1), (512, 1), (2048, 1), (1536, 1), (1024, 0)):
             if n < 16384 and nb != 1024: continue
             eng.set("nb", nb); eng.set("lookahead", la)
             best = 1e30
@@ -97,6 +97,11 @@ if "fit" in what:
         t["potrs_vec"] = ev(lambda: eng.potrs_vec(K, dinv, yd), reps=2)
         Kq = eng.cov_build(st.spec, xq, xd)
         t["trsm300"] = ev(lambda: eng.trsm_rlt(K, dinv, Kq), reps=2)
+        t["cross_build"] = ev(lambda: eng.cov_build(st.spec, xq, xd, out=Kq), reps=2)
+        t["tail_mean"] = ev(lambda: eng.predict_tail(Kq=Kq, alpha=st.alpha), reps=2)
+        kd = eng.cov_diag(st.spec, xq)
+        t["tail_var"] = ev(lambda: eng.predict_tail(V=Kq, kdiag=kd), reps=2)
+        t["predict_events"] = ev(lambda: E.predict(st, xq), reps=2)
         print(json.dumps({"op": "fit+predict", "n": n, "fit_s": t1 - t0, "predict_s": t2 - t1, "lml": st.lml,
                           "mean0": float(m[0]), "var0": float(v[0]), "phases_ms": t, "launches": eng.launches}), flush=True)
         del K, st
