@@ -1,0 +1,180 @@
+"""gpytorch.models.ExactGP backed by the CUDA engine.
+
+Replaces GPyTorch's ExactGP.__call__ + DefaultPredictionStrategy (reached from
+/root/reference/src/batt_models/battcellgp_full.py:173 and /root/reference/src/gp/standard_models.py:41):
+  eval mode : (cached) fit on the training data -> K_*N alpha for the mean; the variance / covariance solve
+              V = K_*N L^-T runs lazily when ``.variance`` / ``._covar`` is read.
+  train mode: returns the prior over the training inputs (consumed by ExactMarginalLogLikelihood).
+The exact Cholesky path is always taken (DESIGN.md "Semantics vs GPyTorch defaults").
+"""
+from __future__ import annotations
+
+import math
+import warnings
+from typing import Optional
+
+import torch
+
+from . import settings
+from .. import engine as E
+from .distributions import MultivariateNormal
+from .kernels import Kernel, LazyKernelMatrix, bind_spec, compute_device, dense_cov, dense_cov_diag, _stage
+from .likelihoods import GaussianLikelihood
+from .module import Module
+from .utils.warnings import GPInputWarning
+
+
+class GP(Module):
+    pass
+
+
+class PosteriorCovariance:
+    """Lazy posterior covariance of the latent f at the query points: k** - V V^T, V = K_*N L^-T (no noise added --
+    recursive_gp.py:120 "add no noise_var to be consistent with gpytorch")."""
+
+    def __init__(self, model, state: E.FitState, kernel: Kernel, xq: torch.Tensor, Kq: torch.Tensor, out_dtype, out_device):
+        self.model, self.state, self.kernel, self.xq, self.Kq = model, state, kernel, xq, Kq
+        self.out_dtype, self.out_device = out_dtype, out_device
+        self._V: Optional[torch.Tensor] = None
+
+    @property
+    def shape(self):
+        m = self.xq.shape[0]
+        return torch.Size([m, m])
+
+    def _solve(self):
+        if self._V is None:
+            eng = E.get_engine(self.state.x.device)
+            self._V = eng.trsm_rlt(self.state.L, self.state.dinv, self.Kq)      # in place: Kq -> V
+            self.Kq = None
+        return self._V
+
+    def diagonal(self, *a, **k):
+        eng = E.get_engine(self.state.x.device)
+        V = self._solve()
+        kd = dense_cov_diag(self.kernel, self.xq).detach().to(device=V.device, dtype=torch.float64)
+        _, var = eng.predict_tail(V=V, kdiag=kd.contiguous(), min_var=-math.inf)   # clamping happens in .variance
+        return var.to(device=self.out_device, dtype=self.out_dtype)
+
+    diag = diagonal
+
+    def to_dense(self):
+        eng = E.get_engine(self.state.x.device)
+        V = self._solve()
+        m = self.xq.shape[0]
+        C = E.alloc_matrix(m, m, V.device)
+        C.copy_(dense_cov(self.kernel, self.xq, self.xq))
+        eng.gemm_nt(V, V, C, alpha=-1.0, beta=1.0)
+        return C.to(device=self.out_device, dtype=self.out_dtype)
+
+    evaluate = to_dense
+
+    def detach(self):
+        return self.to_dense().detach()
+
+    def cpu(self):
+        return self.to_dense().cpu()
+
+    def numpy(self):
+        return self.to_dense().cpu().numpy()
+
+
+class ExactGP(GP):
+    def __init__(self, train_inputs, train_targets, likelihood):
+        if train_inputs is not None and torch.is_tensor(train_inputs):
+            train_inputs = (train_inputs,)
+        if train_inputs is not None and not all(torch.is_tensor(t) for t in train_inputs):
+            raise RuntimeError("Train inputs must be a tensor, or a list/tuple of tensors")
+        if not isinstance(likelihood, GaussianLikelihood):
+            raise RuntimeError("ExactGP can only handle Gaussian likelihoods")
+        super().__init__()
+        self.train_inputs = None if train_inputs is None else tuple(t.unsqueeze(-1) if t.dim() == 1 else t for t in train_inputs)
+        self.train_targets = train_targets
+        self.likelihood = likelihood
+        self.prediction_strategy = None       # (signature, FitState, kernel)
+
+    # nn.Module.to()/cuda()/double() must also move the training data (GPyTorch's ExactGP._apply)
+    def _apply(self, fn, *a, **k):
+        if self.train_inputs is not None:
+            self.train_inputs = tuple(fn(t) for t in self.train_inputs)
+            self.train_targets = fn(self.train_targets)
+        self.prediction_strategy = None
+        return super()._apply(fn, *a, **k)
+
+    def train(self, mode=True):
+        if mode:
+            self.prediction_strategy = None
+        return super().train(mode)
+
+    def set_train_data(self, inputs=None, targets=None, strict=True):
+        if inputs is not None:
+            if torch.is_tensor(inputs):
+                inputs = (inputs,)
+            self.train_inputs = tuple(t.unsqueeze(-1) if t.dim() == 1 else t for t in inputs)
+        if targets is not None:
+            self.train_targets = targets
+        self.prediction_strategy = None
+
+    def forward(self, *x):
+        raise NotImplementedError
+
+    # ------------------------------------------------------------------------------------------------
+    def _signature(self):
+        ps = [p.detach().reshape(-1).to(torch.float64) for p in self.parameters()]
+        return tuple(torch.cat(ps).tolist()) if ps else ()
+
+    def _fit_state(self):
+        sig = self._signature()
+        if self.prediction_strategy is not None and self.prediction_strategy[0] == sig:
+            return self.prediction_strategy[1], self.prediction_strategy[2]
+        train_x = self.train_inputs[0]
+        prior = self.forward(*self.train_inputs)
+        cov = prior._covar
+        if not isinstance(cov, LazyKernelMatrix):
+            raise RuntimeError("ExactGP.forward must return MultivariateNormal(mean, self.covar_module(x))")
+        kernel = cov.kernel
+        dev = compute_device(train_x)
+        x64 = _stage(train_x, dev)
+        resid = _stage(self.train_targets - prior.mean, dev)
+        noise = float(self.likelihood.noise.detach().reshape(-1)[0])
+        binding = bind_spec(kernel, train_x.shape[-1])
+        if binding is not None:
+            st = E.fit(binding.to_spec(), x64, resid, noise)
+        else:
+            def kbuilder(out, nz):
+                k = dense_cov(kernel, train_x, train_x).to(device=dev, dtype=torch.float64)
+                out.copy_(k)
+                out.diagonal().add_(nz)
+            st = E.fit(E.KernelSpec([]), x64, resid, noise, kbuilder=kbuilder)
+        self.prediction_strategy = (sig, st, kernel)
+        return st, kernel
+
+    def __call__(self, *args, **kwargs):
+        inputs = [a.unsqueeze(-1) if a.dim() == 1 else a for a in args]
+        if self.training:
+            if self.train_inputs is None:
+                raise RuntimeError("train_inputs, train_targets cannot be None in training mode. Call .eval() for prior "
+                                   "predictions, or call .set_train_data() to add training data.")
+            if settings.debug.on():
+                if not all(torch.equal(a, b) for a, b in zip(self.train_inputs, inputs)):
+                    raise RuntimeError("You must train on the training inputs!")
+            return self.forward(*inputs, **kwargs)
+        if self.train_inputs is None or self.train_targets is None:
+            return self.forward(*inputs, **kwargs)       # prior mode
+        if settings.debug.on() and all(a.shape == b.shape and torch.equal(a, b) for a, b in zip(self.train_inputs, inputs)):
+            warnings.warn("The input matches the stored training data. Did you forget to call model.train()?", GPInputWarning)
+        xq = inputs[0]
+        st, kernel = self._fit_state()
+        test_prior = self.forward(*inputs, **kwargs)
+        dev = st.x.device
+        eng = E.get_engine(dev)
+        binding = bind_spec(kernel, xq.shape[-1])
+        xq64 = _stage(xq, dev)
+        if binding is not None:
+            Kq = eng.cov_build(binding.to_spec(), xq64, st.x)
+        else:
+            Kq = E.alloc_matrix(xq.shape[0], st.x.shape[0], dev)
+            Kq.copy_(dense_cov(kernel, xq, self.train_inputs[0]).to(device=dev, dtype=torch.float64))
+        mean, _ = eng.predict_tail(Kq=Kq, alpha=st.alpha)
+        mean = mean.to(device=xq.device, dtype=xq.dtype) + test_prior.mean
+        return MultivariateNormal(mean, PosteriorCovariance(self, st, kernel, xq, Kq, xq.dtype, xq.device))
