@@ -56,6 +56,9 @@ SIGNATURES = {
     "bgp_trsm_rlt": (C.c_int, [_P, _P, _I64, _I64, _P, _P, _I64, _I64, _P]),
     "bgp_predict_tail": (C.c_int, [_P, _I64, _I64, _P, _I64, _P, _P, _I64, _P, _D, _P, _P, _P]),
     "bgp_lml": (C.c_int, [_P, _P, _I64, _D, C.POINTER(_D), _P]),
+    "bgp_trsv": (C.c_int, [_P, _P, _I64, _I64, _P, _P, C.c_int, _P]),
+    "bgp_gemv_t": (C.c_int, [_P, _P, _I64, _I64, _I64, _P, _P, _D, _P]),
+    "bgp_rowsumsq": (C.c_int, [_P, _P, _I64, _I64, _I64, _P, C.c_int, _P]),
     "bgp_potri": (C.c_int, [_P, _P, _I64, _I64, _P, _P, _I64, _P]),
     "bgp_lml_grad": (C.c_int, [_P, _SPEC, _P, _I64, _I64, _P, _I64, _P, _P, _P]),
 }

@@ -20,6 +20,8 @@ int trsv_lower_t(Ctx*, const double*, int64_t, int64_t, const double*, double*, 
 int dot(Ctx*, const double*, const double*, int64_t, double*, double*, cudaStream_t);
 int predict_tail(Ctx*, int64_t, int64_t, const double*, int64_t, const double*, const double*, int64_t, const double*,
                  double, double*, double*, cudaStream_t);
+int gemv_t(Ctx*, const double*, int64_t, int64_t, int64_t, const double*, double*, double, cudaStream_t);
+int rowsumsq(Ctx*, const double*, int64_t, int64_t, int64_t, double*, int, cudaStream_t);
 int potri(Ctx*, double*, int64_t, int64_t, const double*, double*, int64_t, cudaStream_t);
 int lml_grad(Ctx*, const bgp_kernel_spec*, const double*, int64_t, int64_t, const double*, int64_t, const double*,
              double*, cudaStream_t);
@@ -262,6 +264,27 @@ int bgp_lml(bgp_ctx* c, const double* z, int64_t n, double logdet, double* lml_h
     }
     *lml_host = -0.5 * zz - 0.5 * logdet - 0.5 * (double)n * log(2.0 * M_PI);
     return 0;
+}
+
+int bgp_trsv(bgp_ctx* c, const double* L, int64_t n, int64_t ldl, const double* dinv, double* b, int trans, void* stream) {
+    CTX_OR_FAIL(c);
+    if (n == 0) return 0;
+    if (!L || !dinv || !b || n < 0 || ldl < n) return BGP_E_ARG;
+    return trans ? trsv_lower_t(ctx, L, n, ldl, dinv, b, b, (cudaStream_t)stream)
+                 : trsv_lower(ctx, L, n, ldl, dinv, b, b, (cudaStream_t)stream);
+}
+
+int bgp_gemv_t(bgp_ctx* c, const double* A, int64_t rows, int64_t cols, int64_t lda, const double* v, double* y,
+               double alpha, void* stream) {
+    CTX_OR_FAIL(c);
+    if (rows < 0 || cols < 0 || (rows > 0 && cols > 0 && (!A || !v || !y || lda < cols))) return BGP_E_ARG;
+    return gemv_t(ctx, A, rows, cols, lda, v, y, alpha, (cudaStream_t)stream);
+}
+
+int bgp_rowsumsq(bgp_ctx* c, const double* V, int64_t m, int64_t n, int64_t ldv, double* out, int accumulate, void* stream) {
+    CTX_OR_FAIL(c);
+    if (m < 0 || n < 0 || (m > 0 && (!V || !out || ldv < n))) return BGP_E_ARG;
+    return rowsumsq(ctx, V, m, n, ldv, out, accumulate, (cudaStream_t)stream);
 }
 
 int bgp_potri(bgp_ctx* c, double* L, int64_t n, int64_t ldl, const double* dinv, double* work, int64_t ldw,

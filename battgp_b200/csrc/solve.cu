@@ -238,6 +238,63 @@ int dot(Ctx* ctx, const double* a, const double* b, int64_t n, double* partial /
     return 0;
 }
 
+// y[c] += alpha * sum_r A[r][c] v[r]   (A [rows, cols] row-major): 128 columns x 4 row-quarters per CTA
+__global__ void __launch_bounds__(512)
+gemv_t_kernel(const double* __restrict__ A, int64_t rows, int64_t cols, int64_t lda, const double* __restrict__ v,
+              double* __restrict__ y, double alpha) {
+    __shared__ double part[4][LEAF];
+    const int tid = threadIdx.x, cl = tid & (LEAF - 1), q = tid >> 7;
+    const int64_t c = (int64_t)blockIdx.x * LEAF + cl;
+    const int64_t rq = (rows + 3) / 4, r0 = q * rq, r1 = min(rows, r0 + rq);
+    double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+    if (c < cols) {
+        const double* ap = A + c;
+        int64_t r = r0;
+        for (; r + 3 < r1; r += 4) {
+            const double a0 = ap[r * lda], a1 = ap[(r + 1) * lda], a2 = ap[(r + 2) * lda], a3 = ap[(r + 3) * lda];
+            s0 = fma(a0, v[r], s0); s1 = fma(a1, v[r + 1], s1); s2 = fma(a2, v[r + 2], s2); s3 = fma(a3, v[r + 3], s3);
+        }
+        for (; r < r1; r++) s0 = fma(ap[r * lda], v[r], s0);
+    }
+    part[q][cl] = (s0 + s1) + (s2 + s3);
+    __syncthreads();
+    if (q == 0 && c < cols) y[c] += alpha * ((part[0][cl] + part[1][cl]) + (part[2][cl] + part[3][cl]));
+}
+
+int gemv_t(Ctx* ctx, const double* A, int64_t rows, int64_t cols, int64_t lda, const double* v, double* y, double alpha,
+           cudaStream_t st) {
+    if (rows <= 0 || cols <= 0) return 0;
+    gemv_t_kernel<<<(unsigned)((cols + LEAF - 1) / LEAF), 512, 0, st>>>(A, rows, cols, lda, v, y, alpha);
+    BGP_LAUNCH_OK(ctx);
+    return 0;
+}
+
+// out[i] = (accumulate ? out[i] : 0) + sum_j V[i][j]^2
+__global__ void __launch_bounds__(256)
+rowsumsq_kernel(const double* __restrict__ V, int64_t n, int64_t ldv, double* __restrict__ out, int accumulate) {
+    __shared__ double red[8];
+    const int64_t i = blockIdx.x;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const double* vp = V + i * ldv;
+    double s = 0.0;
+    for (int64_t j = tid; j < n; j += 256) { const double v = vp[j]; s = fma(v, v, s); }
+    s = warp_sum(s);
+    if (lane == 0) red[warp] = s;
+    __syncthreads();
+    if (tid == 0) {
+        double t = 0.0;
+        for (int w = 0; w < 8; w++) t += red[w];
+        out[i] = (accumulate ? out[i] : 0.0) + t;
+    }
+}
+
+int rowsumsq(Ctx* ctx, const double* V, int64_t m, int64_t n, int64_t ldv, double* out, int accumulate, cudaStream_t st) {
+    if (m <= 0) return 0;
+    rowsumsq_kernel<<<(unsigned)m, 256, 0, st>>>(V, n, ldv, out, accumulate);
+    BGP_LAUNCH_OK(ctx);
+    return 0;
+}
+
 int predict_tail(Ctx* ctx, int64_t m, int64_t n, const double* Kq, int64_t ldk, const double* alpha, const double* V,
                  int64_t ldv, const double* kdiag, double min_var, double* mean, double* var, cudaStream_t st) {
     if (m <= 0) return 0;

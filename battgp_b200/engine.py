@@ -240,6 +240,30 @@ class Engine:
         _lib.check(rc, "bgp_predict_tail")
         return mean, var
 
+    # ------------------------------------------------------------------ sharded building blocks
+    def potrf_block(self, A: torch.Tensor, info_dev: torch.Tensor, logdet_dev: torch.Tensor) -> torch.Tensor:
+        """Asynchronous in-place Cholesky of one diagonal block; returns its 128-block inverses."""
+        nb = A.shape[0]
+        dinv = torch.empty(int(self.L.bgp_potrf_dinv_elems(nb)), dtype=torch.float64, device=self.device)
+        rc = self.L.bgp_potrf_block(self.h, _ptr(A), nb, self._ld(A), _ptr(dinv), _ptr(info_dev), _ptr(logdet_dev), self._stream())
+        _lib.check(rc, "bgp_potrf_block")
+        return dinv
+
+    def trsv(self, Lm: torch.Tensor, dinv: torch.Tensor, b: torch.Tensor, trans: bool = False) -> torch.Tensor:
+        _lib.check(self.L.bgp_trsv(self.h, _ptr(Lm), Lm.shape[0], self._ld(Lm), _ptr(dinv), _ptr(b), 1 if trans else 0,
+                                   self._stream()), "bgp_trsv")
+        return b
+
+    def gemv_t(self, A: torch.Tensor, v: torch.Tensor, y: torch.Tensor, alpha: float = 1.0) -> torch.Tensor:
+        _lib.check(self.L.bgp_gemv_t(self.h, _ptr(A), A.shape[0], A.shape[1], self._ld(A), _ptr(v), _ptr(y), float(alpha),
+                                     self._stream()), "bgp_gemv_t")
+        return y
+
+    def rowsumsq(self, V: torch.Tensor, out: torch.Tensor, accumulate: bool = False) -> torch.Tensor:
+        _lib.check(self.L.bgp_rowsumsq(self.h, _ptr(V), V.shape[0], V.shape[1], self._ld(V), _ptr(out), 1 if accumulate else 0,
+                                       self._stream()), "bgp_rowsumsq")
+        return out
+
     # ------------------------------------------------------------------ K8
     def lml(self, z: torch.Tensor, logdet: float) -> float:
         out = C.c_double(0.0)

@@ -285,6 +285,7 @@ def main():
     ap.add_argument("--workload", default="per_gpu", choices=["per_gpu", "sharded"])
     ap.add_argument("--ref-n", type=int, default=10000, help="sample size of the CPU arm / cpu_baseline")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--nb", type=int, default=1024, help="stripe height of the sharded workload")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args, args.gpus)

@@ -145,6 +145,13 @@ int bgp_lml_grad(bgp_ctx* ctx, const bgp_kernel_spec* spec, const double* X, int
  * factor one nb x nb diagonal block (nb multiple of 128, <= 4096): potrf + all 128-block inverses.  async. */
 int bgp_potrf_block(bgp_ctx* ctx, double* A, int64_t nb, int64_t lda, double* dinv, int32_t* info_dev,
                     double* logdet_dev, void* stream);
+/* in-place single right-hand-side solve with one factored block: L x = b (trans = 0) or L^T x = b (trans != 0) */
+int bgp_trsv(bgp_ctx* ctx, const double* L, int64_t n, int64_t ldl, const double* dinv, double* b, int trans, void* stream);
+/* y[0:cols] += alpha * A^T v for a row-block A [rows, lda] (back-substitution contributions of a block row of L) */
+int bgp_gemv_t(bgp_ctx* ctx, const double* A, int64_t rows, int64_t cols, int64_t lda, const double* v, double* y,
+               double alpha, void* stream);
+/* out[i] = (accumulate ? out[i] : 0) + |V[i,:]|^2  (partial predictive-variance sums of a column shard) */
+int bgp_rowsumsq(bgp_ctx* ctx, const double* V, int64_t m, int64_t n, int64_t ldv, double* out, int accumulate, void* stream);
 
 #ifdef __cplusplus
 }

@@ -1,0 +1,102 @@
+"""GPU: the sharded GP's block operations through the C-ABI (CudaOps).  With one visible GPU the schedule runs with
+P = 1 (every stripe local, no collective); with >= 2 GPUs a 2-rank NCCL run is compared against the single-GPU engine."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import gp_oracle as orc
+
+pytestmark = pytest.mark.gpu
+
+
+def _t(a, dev="cuda:0"):
+    return torch.tensor(np.ascontiguousarray(a), dtype=torch.float64, device=dev)
+
+
+@pytest.mark.parametrize("n,nb", [(1000, 256), (3000, 512), (2500, 1024)])
+def test_sharded_single_rank_matches_oracle_and_engine(eng, n, nb):
+    from battgp_b200 import engine as E
+    from battgp_b200.sharded import ShardedGP
+    x, y = orc.synth_field_data(n, seed=5)
+    xq = orc.query_grid(x)
+    gp = ShardedGP(E.battgp_spec(), _t(x), _t(y), 2.33e-6, nb=nb).fit()
+    mean, var = gp.predict(_t(xq))
+    f = orc.fit(orc.battgp_spec(), x, y, 2.33e-6)
+    mr, vr = orc.predict(orc.battgp_spec(), x, f, xq)
+    assert abs(gp.lml - f.lml) < 1e-9 * abs(f.lml)
+    assert np.linalg.norm(gp.alpha.cpu().numpy() - f.alpha) / np.linalg.norm(f.alpha) < 1e-7
+    np.testing.assert_allclose(mean.cpu().numpy(), mr, rtol=1e-7)
+    np.testing.assert_allclose(var.cpu().numpy(), vr, rtol=1e-6)
+    # the stripes hold the same factor as the monolithic engine
+    st = E.fit(E.battgp_spec(), _t(x), _t(y), 2.33e-6)
+    L = torch.tril(st.L)
+    for i in gp.owned:
+        b0, e = gp.b0(i), gp.e(i)
+        blk = gp.rows[i].clone()
+        ref = L[b0:e, :e]
+        blk[:, b0:e] = torch.tril(blk[:, b0:e])
+        assert ((blk - ref).norm() / ref.norm()).item() < 1e-10
+
+
+def test_trsv_gemv_t_rowsumsq_blocks(eng):
+    rng = np.random.default_rng(0)
+    n = 700
+    a = rng.normal(size=(n, n)); k = a @ a.T + n * np.eye(n)
+    A = _t(k)
+    info, _, dinv = eng.potrf(A)
+    assert info == 0
+    L = np.tril(A.cpu().numpy())
+    b = rng.normal(size=n)
+    import scipy.linalg as sla
+    x1 = eng.trsv(A, dinv, _t(b), False).cpu().numpy()
+    x2 = eng.trsv(A, dinv, _t(b), True).cpu().numpy()
+    assert np.linalg.norm(x1 - sla.solve_triangular(L, b, lower=True)) / np.linalg.norm(x1) < 1e-10
+    assert np.linalg.norm(x2 - sla.solve_triangular(L, b, lower=True, trans="T")) / np.linalg.norm(x2) < 1e-10
+    M = rng.normal(size=(333, 517)); v = rng.normal(size=333); yv = rng.normal(size=517)
+    out = eng.gemv_t(_t(M), _t(v), _t(yv), -0.5).cpu().numpy()
+    np.testing.assert_allclose(out, yv - 0.5 * M.T @ v, rtol=1e-12, atol=1e-12)
+    acc = _t(np.ones(333))
+    eng.rowsumsq(_t(M), acc, True)
+    np.testing.assert_allclose(acc.cpu().numpy(), 1 + (M ** 2).sum(1), rtol=1e-13)
+
+
+def _nccl_worker(rank, world, port, n, nb, q):
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    try:
+        from battgp_b200 import engine as E
+        from battgp_b200.sharded import ShardedGP
+        x, y = orc.synth_field_data(n, seed=5)
+        dev = f"cuda:{rank}"
+        gp = ShardedGP(E.battgp_spec(), _t(x, dev), _t(y, dev), 2.33e-6, nb=nb).fit()
+        mean, var = gp.predict(_t(orc.query_grid(x), dev))
+        q.put((rank, gp.lml, mean.cpu().numpy(), var.cpu().numpy(), gp.bytes_received))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs two GPUs")
+def test_sharded_two_ranks_nccl_matches_oracle():
+    import torch.multiprocessing as mp
+    n, nb, world = 5000, 512, 2
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    ps = [ctx.Process(target=_nccl_worker, args=(r, world, port, n, nb, q)) for r in range(world)]
+    [p.start() for p in ps]
+    res = [q.get(timeout=300) for _ in range(world)]
+    [p.join(timeout=60) for p in ps]
+    x, y = orc.synth_field_data(n, seed=5)
+    f = orc.fit(orc.battgp_spec(), x, y, 2.33e-6)
+    mr, vr = orc.predict(orc.battgp_spec(), x, f, orc.query_grid(x))
+    for rank, lml, mean, var, recv in res:
+        assert abs(lml - f.lml) < 1e-9 * abs(f.lml)
+        np.testing.assert_allclose(mean, mr, rtol=1e-7)
+        np.testing.assert_allclose(var, vr, rtol=1e-6)
+        assert recv > 0
