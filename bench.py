@@ -281,10 +281,11 @@ def main():
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--n", type=int, default=40000)
+    ap.add_argument("--size", dest="n", type=int, default=40000, help="training points per GP")
     ap.add_argument("--workload", default="per_gpu", choices=["per_gpu", "sharded"])
     ap.add_argument("--ref-n", type=int, default=10000, help="sample size of the CPU arm / cpu_baseline")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--verify", action="store_true", help="sharded workload: also report the matrix-free residual |K alpha - y|/|y|")
     ap.add_argument("--nb", type=int, default=1024, help="stripe height of the sharded workload")
     args = ap.parse_args()
     if args.impl == "reference":

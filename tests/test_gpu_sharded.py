@@ -30,6 +30,7 @@ def test_sharded_single_rank_matches_oracle_and_engine(eng, n, nb):
     assert np.linalg.norm(gp.alpha.cpu().numpy() - f.alpha) / np.linalg.norm(f.alpha) < 1e-7
     np.testing.assert_allclose(mean.cpu().numpy(), mr, rtol=1e-7)
     np.testing.assert_allclose(var.cpu().numpy(), vr, rtol=1e-6)
+    assert gp.residual() < 1e-8
     # the stripes hold the same factor as the monolithic engine
     st = E.fit(E.battgp_spec(), _t(x), _t(y), 2.33e-6)
     L = torch.tril(st.L)

@@ -84,6 +84,7 @@ def _worker(rank, world, port, n, nb, q):
         gp.fit()
         mean, var = gp.predict(torch.from_numpy(xq))
         owned_ok = all(i % world == rank for i in gp.owned) and sum(1 for _ in gp.owned) in (gp.nblk // world, gp.nblk // world + 1)
+        assert gp.residual() < 1e-8
         q.put((rank, gp.lml, gp.alpha.numpy(), mean.numpy(), var.numpy(), owned_ok, gp.bytes_received))
     finally:
         dist.destroy_process_group()

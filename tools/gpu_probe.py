@@ -57,7 +57,7 @@ if "potrf" in what:
         K = E.alloc_matrix(n, n, dev)
         msb = ev(lambda: eng.cov_build(spec, xd, noise=2.33e-6, symmetric=True, out=K))
         print(json.dumps({"op": "cov_build_sym", "n": n, "ms": msb, "GBps": 8 * n * (n + 1) / 2 / msb * 1e-6}), flush=True)
-        for nb, la in ((1024, 1), (512, 1), (2048, 1), (1536, 1), (1024, 0)):
+        for nb, la in ((1024, 1), (2048, 1), (1024, 0)):
             if n < 16384 and nb != 1024: continue
             eng.set("nb", nb); eng.set("lookahead", la)
             best = 1e30
@@ -105,4 +105,25 @@ if "fit" in what:
         print(json.dumps({"op": "fit+predict", "n": n, "fit_s": t1 - t0, "predict_s": t2 - t1, "lml": st.lml,
                           "mean0": float(m[0]), "var0": float(v[0]), "phases_ms": t, "launches": eng.launches}), flush=True)
         del K, st
+        torch.cuda.empty_cache()
+
+if "grad" in what:
+    for n, mk in ((20000, "battgp"), (40000, "battgp"), (40000, "matern_periodic")):
+        x, y = synth_field_data(n, 0)
+        xd, yd = torch.tensor(x, device=dev), torch.tensor(y, device=dev)
+        spec = E.battgp_spec() if mk == "battgp" else E.matern_periodic_spec()
+        K = E.alloc_matrix(n, n, dev); W = E.alloc_matrix(n, n, dev)
+        res = {}
+        for r in range(2):
+            torch.cuda.synchronize(); t0 = time.perf_counter()
+            st = E.fit(spec, xd, yd, 2.33e-6, K_out=K)
+            torch.cuda.synchronize(); t1 = time.perf_counter()
+            eng.potri(st.L, st.dinv, W)
+            torch.cuda.synchronize(); t2 = time.perf_counter()
+            g = eng.lml_grad(spec, 2.33e-6, xd, st.L, st.alpha)
+            torch.cuda.synchronize(); t3 = time.perf_counter()
+            res = {"fit_s": t1 - t0, "potri_s": t2 - t1, "grad_s": t3 - t2, "pass_s": t3 - t0}
+        print(json.dumps({"op": "lml+grad pass", "n": n, "kernel": mk, **res, "potri_tflops": 0.83 * n ** 3 / res["potri_s"] * 1e-12,
+                          "grad": [float(v) for v in g.cpu()]}), flush=True)
+        del K, W, st
         torch.cuda.empty_cache()
