@@ -45,10 +45,14 @@ SIGNATURES = {
     "bgp_ctx_create": (C.c_int, [C.c_int, C.POINTER(_P)]),
     "bgp_ctx_destroy": (None, [_P]),
     "bgp_ctx_set": (C.c_int, [_P, C.c_char_p, C.c_int]),
+    "bgp_potrf_workspace_bytes": (_I64, [_P, _I64]),
+    "bgp_ctx_set_workspace": (C.c_int, [_P, _P, _I64]),
     "bgp_ctx_launches": (_I64, [_P]),
     "bgp_cov_build": (C.c_int, [_P, _SPEC, _P, _I64, _I64, _P, _I64, _I64, _P, _I64, C.c_int, _P]),
     "bgp_cov_diag": (C.c_int, [_P, _SPEC, _P, _I64, _I64, _P, _P]),
     "bgp_gemm_nt": (C.c_int, [_P, _I64, _I64, _I64, _D, _P, _I64, _P, _I64, _D, _P, _I64, C.c_int, _I64, _I64, _P]),
+    "bgp_gemm_nt_i8_work_bytes": (_I64, [_I64, _I64, _I64]),
+    "bgp_gemm_nt_i8": (C.c_int, [_P, _I64, _I64, _I64, _D, _P, _I64, _P, _I64, _P, _I64, C.c_int, _I64, _I64, _P, _I64, _P]),
     "bgp_potrf_dinv_elems": (_I64, [_I64]),
     "bgp_potrf": (C.c_int, [_P, _P, _I64, _I64, _P, C.POINTER(_D), _P]),
     "bgp_potrf_block": (C.c_int, [_P, _P, _I64, _I64, _P, _P, _P, _P]),

@@ -22,6 +22,10 @@ int predict_tail(Ctx*, int64_t, int64_t, const double*, int64_t, const double*, 
                  double, double*, double*, cudaStream_t);
 int gemv_t(Ctx*, const double*, int64_t, int64_t, int64_t, const double*, double*, double, cudaStream_t);
 int rowsumsq(Ctx*, const double*, int64_t, int64_t, int64_t, double*, int, cudaStream_t);
+int64_t oz_slice_buffer_bytes(int64_t rows, int64_t K);
+int oz_slice(Ctx*, const double*, int64_t, int64_t, int64_t, void*, cudaStream_t);
+int oz_gemm(Ctx*, const void*, int64_t, int64_t, const void*, int64_t, int64_t, int64_t, int64_t, int64_t, double, double*,
+            int64_t, int, int64_t, int64_t, cudaStream_t);
 int potri(Ctx*, double*, int64_t, int64_t, const double*, double*, int64_t, cudaStream_t);
 int lml_grad(Ctx*, const bgp_kernel_spec*, const double*, int64_t, int64_t, const double*, int64_t, const double*,
              double*, cudaStream_t);
@@ -40,11 +44,23 @@ struct DeviceGuard {
     ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
 };
 
+// panel width: "nb" knob, or (nb == 0) automatic -- wide panels amortise the fixed per-tile cost of the int8 path
+static inline int64_t effective_nb(const Ctx* ctx, int64_t n) {
+    if (ctx->nb > 0) return ctx->nb;
+    return (ctx->ozaki && n >= 30000) ? 2048 : 1024;
+}
+
 // Right-looking over NB-wide panels with one panel of look-ahead (see potrf.cu header comment).
 static int potrf_driver(Ctx* ctx, double* A, int64_t n, int64_t lda, double* dinv, cudaStream_t mainst) {
-    const int64_t NB = ctx->nb;
+    const int64_t NB = effective_nb(ctx, n);
     if (!ctx->lookahead || n <= 2 * NB) return potrf_rec(ctx, A, n, lda, dinv, 0, mainst);
     cudaStream_t P = ctx->panel_stream;
+    // int8/tcgen05 trailing updates (ozaki.cu): two slice buffers (panel k is still being read by T_k on the caller's
+    // stream while panel k+1 is sliced on the panel stream)
+    const int64_t ozbytes = ((oz_slice_buffer_bytes(n - NB, NB) + 255) / 256) * 256;
+    const bool oz = ctx->ozaki && ctx->ws && (NB % 64 == 0) && ((lda & 1) == 0) && (((uintptr_t)A & 15) == 0) &&
+                    (((uintptr_t)ctx->ws & 255) == 0) && ctx->ws_bytes >= 2 * ozbytes;
+    void* ozbuf[2] = {ctx->ws, reinterpret_cast<char*>(ctx->ws) + ozbytes};
     BGP_CUDA_OK(cudaEventRecord(ctx->ev_fork, mainst));
     BGP_CUDA_OK(cudaStreamWaitEvent(P, ctx->ev_fork, 0));
     const int64_t npanels = (n + NB - 1) / NB;
@@ -58,20 +74,32 @@ static int potrf_driver(Ctx* ctx, double* A, int64_t n, int64_t lda, double* din
         // ---- P_k (panel stream): bring column block k up to date with panel k-1, factor it, solve the rows below
         if (k >= 1) {
             if (k >= 2) BGP_CUDA_OK(cudaStreamWaitEvent(P, ctx->ev_trail[(k - 2) % 3], 0));
-            const double* Lp = A + k0 * lda + (k0 - NB);     // rows k0.., columns of panel k-1
-            GemmArgs g{Lp, lda, Lp, lda, Akk, lda, (int)(n - k0), (int)nbk, (int)NB, -1.0, 1.0, 1, 0, 0};
-            if ((rc = gemm_nt(ctx, g, P))) return rc;
+            if (oz) {
+                // panel k-1 was sliced (rows k0.. of it are rows 0.. of its slice buffer)
+                if ((rc = oz_gemm(ctx, ozbuf[(k - 1) & 1], n - k0, 0, ozbuf[(k - 1) & 1], n - k0, 0, n - k0, nbk, NB, -1.0, Akk, lda,
+                                  1, 0, 0, P))) return rc;
+            } else {
+                const double* Lp = A + k0 * lda + (k0 - NB);     // rows k0.., columns of panel k-1
+                GemmArgs g{Lp, lda, Lp, lda, Akk, lda, (int)(n - k0), (int)nbk, (int)NB, -1.0, 1.0, 1, 0, 0};
+                if ((rc = gemm_nt(ctx, g, P))) return rc;
+            }
         }
         if ((rc = potrf_rec(ctx, Akk, nbk, lda, dinv_k, k0, P))) return rc;
         if (below > 0 && (rc = trsm_rlt_rec(ctx, Akk, nbk, lda, dinv_k, Akk + nbk * lda, below, lda, P))) return rc;
+        if (oz && below > 0 && (rc = oz_slice(ctx, Akk + nbk * lda, below, nbk, lda, ozbuf[k & 1], P))) return rc;
         BGP_CUDA_OK(cudaEventRecord(ctx->ev_panel[k % 2], P));
         // ---- T_k (caller's stream): rank-nbk update of everything right of column block k+1
         const int64_t t0 = k0 + nbk + NB;
         if (t0 < n) {
             BGP_CUDA_OK(cudaStreamWaitEvent(mainst, ctx->ev_panel[k % 2], 0));
-            const double* Lt = A + t0 * lda + k0;
-            GemmArgs g{Lt, lda, Lt, lda, A + t0 * lda + t0, lda, (int)(n - t0), (int)(n - t0), (int)nbk, -1.0, 1.0, 1, 0, 0};
-            if ((rc = gemm_nt(ctx, g, mainst))) return rc;
+            if (oz) {
+                if ((rc = oz_gemm(ctx, ozbuf[k & 1], below, NB, ozbuf[k & 1], below, NB, n - t0, n - t0, nbk, -1.0,
+                                  A + t0 * lda + t0, lda, 1, 0, 0, mainst))) return rc;
+            } else {
+                const double* Lt = A + t0 * lda + k0;
+                GemmArgs g{Lt, lda, Lt, lda, A + t0 * lda + t0, lda, (int)(n - t0), (int)(n - t0), (int)nbk, -1.0, 1.0, 1, 0, 0};
+                if ((rc = gemm_nt(ctx, g, mainst))) return rc;
+            }
             BGP_CUDA_OK(cudaEventRecord(ctx->ev_trail[k % 3], mainst));
         }
     }
@@ -150,13 +178,30 @@ int bgp_ctx_set(bgp_ctx* p, const char* key, int value) {
     if (!p || !key) return BGP_E_ARG;
     Ctx* c = reinterpret_cast<Ctx*>(p);
     if (!strcmp(key, "nb")) {
-        if (value < LEAF || value % LEAF != 0 || value > 8192) return BGP_E_ARG;
+        if (value != 0 && (value < LEAF || value % LEAF != 0 || value > 8192)) return BGP_E_ARG;
         c->nb = value;
         return 0;
     }
     if (!strcmp(key, "lookahead")) { c->lookahead = value ? 1 : 0; return 0; }
+    if (!strcmp(key, "ozaki")) { c->ozaki = value ? 1 : 0; return 0; }
     if (!strcmp(key, "gemm_cfg")) { if (value < 0 || value > 7) return BGP_E_ARG; c->gemm_cfg = value; return 0; }
     return BGP_E_ARG;
+}
+
+int64_t bgp_potrf_workspace_bytes(const bgp_ctx* p, int64_t n) {
+    if (!p || n <= 0) return 0;
+    const Ctx* c = reinterpret_cast<const Ctx*>(p);
+    const int64_t nb = effective_nb(c, n);
+    if (n <= 2 * nb) return 0;
+    return 2 * (((oz_slice_buffer_bytes(n - nb, nb) + 255) / 256) * 256);
+}
+
+int bgp_ctx_set_workspace(bgp_ctx* p, void* ptr, int64_t bytes) {
+    if (!p || bytes < 0 || (bytes > 0 && !ptr)) return BGP_E_ARG;
+    Ctx* c = reinterpret_cast<Ctx*>(p);
+    c->ws = bytes ? ptr : nullptr;
+    c->ws_bytes = bytes;
+    return 0;
 }
 
 int64_t bgp_ctx_launches(const bgp_ctx* p) { return p ? reinterpret_cast<const Ctx*>(p)->launches : 0; }
@@ -285,6 +330,28 @@ int bgp_rowsumsq(bgp_ctx* c, const double* V, int64_t m, int64_t n, int64_t ldv,
     CTX_OR_FAIL(c);
     if (m < 0 || n < 0 || (m > 0 && (!V || !out || ldv < n))) return BGP_E_ARG;
     return rowsumsq(ctx, V, m, n, ldv, out, accumulate, (cudaStream_t)stream);
+}
+
+int64_t bgp_gemm_nt_i8_work_bytes(int64_t M, int64_t N, int64_t K) {
+    return oz_slice_buffer_bytes(M, K) + oz_slice_buffer_bytes(N, K) + 512;
+}
+
+int bgp_gemm_nt_i8(bgp_ctx* c, int64_t M, int64_t N, int64_t K, double alpha, const double* A, int64_t lda, const double* B,
+                   int64_t ldb, double* C, int64_t ldc, int tri, int64_t roff, int64_t coff, void* work, int64_t work_bytes,
+                   void* stream) {
+    CTX_OR_FAIL(c);
+    if (M < 0 || N < 0 || K <= 0 || K % 64 || M > INT_MAX || N > INT_MAX) return BGP_E_ARG;
+    if (M == 0 || N == 0) return 0;
+    if (!A || !B || !C || !work || lda < K || ldb < K || ldc < N || work_bytes < bgp_gemm_nt_i8_work_bytes(M, N, K)) return BGP_E_ARG;
+    if ((uintptr_t)work & 255) return BGP_E_ARG;
+    cudaStream_t st = (cudaStream_t)stream;
+    char* wa = reinterpret_cast<char*>(work);
+    char* wb = wa + ((oz_slice_buffer_bytes(M, K) + 255) / 256) * 256;
+    int rc = oz_slice(ctx, A, M, K, lda, wa, st);
+    if (rc) return rc;
+    const bool same = (A == B && lda == ldb && M == N);
+    if (!same && (rc = oz_slice(ctx, B, N, K, ldb, wb, st))) return rc;
+    return oz_gemm(ctx, wa, M, 0, same ? wa : wb, N, 0, M, N, K, alpha, C, ldc, tri ? 1 : 0, roff, coff, st);
 }
 
 int bgp_potri(bgp_ctx* c, double* L, int64_t n, int64_t ldl, const double* dinv, double* work, int64_t ldw,

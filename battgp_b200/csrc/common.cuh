@@ -19,8 +19,11 @@ struct Ctx {
     int32_t* d_info = nullptr;              // first failing pivot (1-based), INT_MAX when none
     double* d_scal = nullptr;               // [0] logdet accumulator, [1] dot result, [8..] dot partials
     double* d_scratch = nullptr;            // SCRATCH_BYTES of reduction partials (lml_grad)
-    int nb = 1024;
+    int nb = 0;                             // 0 = automatic (api.cu effective_nb)
     int lookahead = 1;
+    int ozaki = 0;                          // 1: big trailing updates of bgp_potrf go through the int8/tcgen05 path
+    void* ws = nullptr;                     // caller-provided scratch (bgp_ctx_set_workspace)
+    int64_t ws_bytes = 0;
     int gemm_cfg = 0;                       // 0 = default big-tile config, else forced variant (probing)
     int64_t launches = 0;
 };

@@ -1,0 +1,359 @@
+// FP64-accurate NT GEMM on the 5th-gen tensor cores by integer slicing (Ozaki scheme I) -- EXPERIMENTAL path.
+//
+// tcgen05 has no f64 kind, so the FP64 DMMA pipe (37 TF/s) bounds gemm_nt.cu.  Here every fp64 operand row is split
+// into 8 signed 7-bit digits against a per-row power-of-two scale,
+//     a = 2^e * ( d0/2^6 + d1/2^13 + ... + d7/2^55 ),   d_s in [-64, 64]  (exact: 55 bits + sign),
+// and  A B^T = sum_{s,t} 2^(eA_i + eB_j - 12 - 7(s+t)) (A_s B_t^T)  is evaluated with EXACT int8 x int8 -> int32
+// tcgen05.mma (kind::i8) products.  Pairs with s+t > 7 are dropped (<= K * 2^-56 relative to rowmax*colmax, the size of
+// fp64's own rounding), leaving 36 products whose partial sums with equal s+t share one int32 accumulator in TMEM
+// (8 accumulators x 64 columns = all 512 TMEM columns of a 128 x 64 tile).  The epilogue reads the 8 accumulators with
+// tcgen05.ld, recombines them in fp64 and applies C += alpha * (...).
+//
+// Kernel structure (one 128x64 tile per CTA, 192 threads):
+//   warp 0  : producer   -- cp.async.bulk (TMA bulk engine) copies of pre-swizzled slice tiles into a 2-stage smem ring,
+//                           completion on mbarriers (expect_tx)
+//   warp 1  : MMA issuer -- one thread issues 72 tcgen05.mma per 64-wide k-block, tcgen05.commit frees the stage
+//   warps 2-5: epilogue  -- tcgen05.ld of the accumulators (one TMEM lane quadrant each), fp64 recombination, C update
+// The slice kernel writes the operand slices to global memory already in the 64-byte-swizzled shared-memory image the
+// UMMA descriptors expect, in [k-block][128-row block][slice] order, so a tile's slices are contiguous bulk copies.
+#include <climits>
+#include "common.cuh"
+
+namespace bgp {
+
+constexpr int OZ_S = 8;
+constexpr int OZ_BM = 128, OZ_BN = 64, OZ_BK = 64;
+constexpr int OZ_STAGES = 2;
+constexpr int OZ_A_STAGE = OZ_S * OZ_BM * OZ_BK;     // 65536 B
+constexpr int OZ_B_STAGE = OZ_S * OZ_BN * OZ_BK;     // 32768 B
+constexpr int OZ_SLICE_TILE = OZ_BM * OZ_BK;         // 8192 B: one slice of a 128-row block for one k-block
+
+// ------------------------------------------------------------------------------------------------ slicing
+__device__ __forceinline__ int oz_swz64(int r8, int kb64) {
+    // Swizzle<2,4,3>: 16-byte chunk index (bits 4-5) ^= row bits 1-2 (address bits 7-8)
+    const int chunk = (kb64 >> 4) ^ ((r8 >> 1) & 3);
+    return r8 * 64 + chunk * 16 + (kb64 & 15);
+}
+
+// grid.x = ceil(rows_pad / 8); block = 512 threads = 8 rows x 64 chunk-threads
+__global__ void __launch_bounds__(512)
+oz_slice_kernel(const double* __restrict__ P, int64_t rows, int64_t K, int64_t ld, int8_t* __restrict__ out,
+                double* __restrict__ ex, int64_t nrb) {
+    __shared__ unsigned long long smax[8];
+    const int tid = threadIdx.x, r8 = tid >> 6, ct = tid & 63;
+    const int64_t row = (int64_t)blockIdx.x * 8 + r8;
+    if (ct == 0) smax[r8] = 0ull;
+    __syncthreads();
+    const int64_t nchunks = K / 16;
+    const bool live = row < rows;
+    double m = 0.0;
+    if (live)
+        for (int64_t c = ct; c < nchunks; c += 64) {
+            const double2* p = reinterpret_cast<const double2*>(P + row * ld + c * 16);
+#pragma unroll
+            for (int i = 0; i < 8; i++) { const double2 v = p[i]; m = fmax(m, fmax(fabs(v.x), fabs(v.y))); }
+        }
+    atomicMax(&smax[r8], (unsigned long long)__double_as_longlong(m));     // non-negative doubles order like integers
+    __syncthreads();
+    const double rowmax = __longlong_as_double((long long)smax[r8]);
+    int e = 0;
+    if (rowmax > 0.0) (void)frexp(rowmax, &e);                             // rowmax = f * 2^e, f in [0.5, 1)
+    if (ct == 0 && row < nrb * 128) ex[row] = scalbn(1.0, e);          // row scale 2^e
+    const int64_t rb = row >> 7;
+    const int rin = (int)(row & 127);
+    for (int64_t c = ct; c < nchunks; c += 64) {
+        uint32_t w[OZ_S][4];
+#pragma unroll
+        for (int s = 0; s < OZ_S; s++) w[s][0] = w[s][1] = w[s][2] = w[s][3] = 0u;
+        if (live) {
+            const double* p = P + row * ld + c * 16;
+#pragma unroll
+            for (int i = 0; i < 16; i++) {
+                double x = scalbn(p[i], -e);                              // |x| < 1, exact
+                double v = rint(x * 64.0);
+                w[0][i >> 2] |= ((uint32_t)(int)v & 255u) << ((i & 3) * 8);
+                x = fma(x, 64.0, -v);                                     // |x| <= 0.5, exact
+#pragma unroll
+                for (int s = 1; s < OZ_S; s++) {
+                    v = rint(x * 128.0);
+                    w[s][i >> 2] |= ((uint32_t)(int)v & 255u) << ((i & 3) * 8);
+                    x = fma(x, 128.0, -v);
+                }
+            }
+        }
+        const int64_t kb = (c * 16) >> 6;
+        const int kin = (int)((c * 16) & 63);
+        int8_t* base = out + ((kb * nrb + rb) * OZ_S) * (int64_t)OZ_SLICE_TILE + (rin >> 3) * 512 + oz_swz64(rin & 7, kin);
+#pragma unroll
+        for (int s = 0; s < OZ_S; s++)
+            *reinterpret_cast<uint4*>(base + (int64_t)s * OZ_SLICE_TILE) = make_uint4(w[s][0], w[s][1], w[s][2], w[s][3]);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ PTX helpers
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                 : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+    return ok != 0;
+}
+// bounded wait: a wrong descriptor must end in a trap (CUDA error), never in a hung GPU
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    for (uint32_t it = 0; it < (1u << 24); ++it)
+        if (mbar_try_wait(bar, parity)) return;
+    __trap();
+}
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+__device__ __forceinline__ uint64_t oz_desc(uint32_t saddr) {
+    // K-major, SWIZZLE_64B (layout type 4), SBO = 512 B (8 rows x 64 B), LBO = 0, descriptor version 1 (sm_100)
+    uint64_t d = 0;
+    d |= (uint64_t)((saddr >> 4) & 0x3FFF);
+    d |= (uint64_t)((512 >> 4) & 0x3FFF) << 32;
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)4 << 61;
+    return d;
+}
+__device__ __forceinline__ void oz_mma_i8(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t accumulate) {
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+                 "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, p;\n\t}"
+                 ::"r"(tmem_d), "l"(da), "l"(db), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void oz_commit(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+                 "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+                 : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+                   "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
+                   "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
+                   "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+                 : "r"(taddr) : "memory");
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile("{\n\t.reg .b32 rx;\n\t.reg .pred px;\n\telect.sync rx|px, 0xffffffff;\n\tselp.u32 %0, 1, 0, px;\n\t}" : "=r"(pred)::"memory");
+    return pred != 0;
+}
+// exact int32 -> double without the (slow) I2F.F64 path: 2^52 + 2^31 + v has v + 2^31 in its low mantissa word
+__device__ __forceinline__ double i32_to_f64(uint32_t v) {
+    return __hiloint2double(0x43300000, (int)(v ^ 0x80000000u)) - 4503601774854144.0;   // 2^52 + 2^31
+}
+
+struct OzArgs {
+    const int8_t* sa; int64_t nrb_a; int64_t arow0;     // slices of A, 128-row blocks in its buffer, first row (mult. of 128)
+    const int8_t* sb; int64_t nrb_b; int64_t brow0;     // slices of B, first row (multiple of 64)
+    const double* exa; const double* exb;               // per-row scales 2^e, indexed like the slice buffers
+    double* C; int64_t ldc;
+    int M, N, K;
+    double alpha;
+    int tri; int64_t roff, coff;
+    int debug_noload;      // experiment: only the first OZ_STAGES k-blocks are really loaded
+};
+
+__global__ void __launch_bounds__(192, 1) oz_mma_kernel(OzArgs g, int tiles_m, int tiles_n) {
+    // grouped raster as in gemm_nt.cu
+    constexpr int GROUP = 8;
+    const int pid = blockIdx.x;
+    const int per_group = GROUP * tiles_n;
+    const int gid = pid / per_group;
+    const int first_m = gid * GROUP;
+    const int gsize = min(tiles_m - first_m, GROUP);
+    const int tm = first_m + (pid % per_group) % gsize;
+    const int tn = (pid % per_group) / gsize;
+    const int m0 = tm * OZ_BM, n0 = tn * OZ_BN;
+    if (g.tri && ((int64_t)n0 + g.coff > (int64_t)m0 + OZ_BM - 1 + g.roff)) return;
+
+    extern __shared__ uint8_t oz_smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(oz_smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint8_t* sA = smem;                                       // [stage][8 slices][128 x 64 B]
+    uint8_t* sB = smem + OZ_STAGES * OZ_A_STAGE;              // [stage][8 slices][64 x 64 B]
+    uint64_t* bars = reinterpret_cast<uint64_t*>(sB + OZ_STAGES * OZ_B_STAGE);
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8);
+    const uint32_t full0 = smem_u32(bars), empty0 = smem_u32(bars + OZ_STAGES), tfull = smem_u32(bars + 2 * OZ_STAGES);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (warp == 0 && lane == 0) {
+        for (int i = 0; i < OZ_STAGES; i++) { mbar_init(full0 + 8 * i, 1); mbar_init(empty0 + 8 * i, 1); }
+        mbar_init(tfull, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem_base = *tmem_slot;
+    const int KB = g.K / OZ_BK;
+
+    // Producer and MMA warps run their loops warp-uniformly (all 32 lanes wait on the barriers, one elected lane
+    // issues): operands then live in uniform registers and no per-lane "waterfall" code is generated around UTCIMMA.
+    if (warp == 0) {
+        const int64_t arb = (g.arow0 + m0) >> 7;
+        const int64_t brb = (g.brow0 + n0) >> 7;
+        const int bhalf = (int)(((g.brow0 + n0) >> 6) & 1);
+        for (int kb = 0; kb < KB; kb++) {
+            const int st = kb % OZ_STAGES;
+            const uint32_t ph = (kb / OZ_STAGES) & 1;
+            mbar_wait(empty0 + 8 * st, ph ^ 1);
+            if (elect_one()) {
+                if (g.debug_noload && kb >= OZ_STAGES) {
+                    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(full0 + 8 * st) : "memory");
+                } else {
+                    mbar_expect_tx(full0 + 8 * st, OZ_A_STAGE + OZ_B_STAGE);
+                    bulk_g2s(smem_u32(sA + st * OZ_A_STAGE), g.sa + ((int64_t)kb * g.nrb_a + arb) * OZ_S * OZ_SLICE_TILE, OZ_A_STAGE,
+                             full0 + 8 * st);
+                    const int8_t* bsrc = g.sb + ((int64_t)kb * g.nrb_b + brb) * OZ_S * OZ_SLICE_TILE + bhalf * 4096;
+#pragma unroll
+                    for (int s = 0; s < OZ_S; s++)
+                        bulk_g2s(smem_u32(sB + st * OZ_B_STAGE + s * 4096), bsrc + (int64_t)s * OZ_SLICE_TILE, 4096, full0 + 8 * st);
+                }
+            }
+            __syncwarp();
+        }
+    } else if (warp == 1) {
+        // kind::i8, D = S32, A/B = signed int8, both K-major, M = 128.  For a fixed A slice s the B slices t = 0..7-s are
+        // adjacent 64-row tiles in shared memory AND their accumulators c = s+t are adjacent 64-column blocks in TMEM, so
+        // they are issued as ONE wide MMA (N up to 256): 12 instead of 36 instructions per k-step and, more importantly,
+        // each A slice is read from shared memory 1-2 times instead of 8-s times (the 128 B/cycle smem port, not the
+        // tensor pipe, limited the 36-MMA form).
+        const uint32_t idesc0 = (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(OZ_BM >> 4) << 24);
+        const uint64_t dzero = oz_desc(0);
+        for (int kb = 0; kb < KB; kb++) {
+            const int st = kb % OZ_STAGES;
+            const uint32_t ph = (kb / OZ_STAGES) & 1;
+            mbar_wait(full0 + 8 * st, ph);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            if (elect_one()) {
+                const uint64_t da0 = dzero + (uint64_t)(smem_u32(sA + st * OZ_A_STAGE) >> 4);
+                const uint64_t db0 = dzero + (uint64_t)(smem_u32(sB + st * OZ_B_STAGE) >> 4);
+#pragma unroll
+                for (int ks = 0; ks < OZ_BK / 32; ks++) {
+#pragma unroll
+                    for (int s = 0; s < OZ_S; s++) {
+                        const uint64_t da = da0 + (uint64_t)((s * OZ_SLICE_TILE + ks * 32) >> 4);
+                        const uint32_t acc = (ks > 0 || s > 0) ? 1u : (kb > 0 ? 1u : 0u);
+#pragma unroll
+                        for (int t0 = 0; t0 + s < OZ_S; t0 += 4) {
+                            const int nt = (OZ_S - s - t0) < 4 ? (OZ_S - s - t0) : 4;     // B slices in this MMA
+                            const uint64_t db = db0 + (uint64_t)((t0 * 4096 + ks * 32) >> 4);
+                            const uint32_t idesc = idesc0 | ((uint32_t)((nt * OZ_BN) >> 3) << 17);
+                            oz_mma_i8(tmem_base + (uint32_t)(s + t0) * OZ_BN, da, db, idesc, acc);
+                        }
+                    }
+                }
+                oz_commit(empty0 + 8 * st);
+                if (kb == KB - 1) oz_commit(tfull);
+            }
+            __syncwarp();
+        }
+    } else {
+        mbar_wait(tfull, 0);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        // All MMAs have completed (tfull), so the operand stages are idle: each epilogue warp uses 32 x 33 doubles of
+        // them to transpose its 32-row x 32-column block -- TMEM hands a thread one ROW (lane), global memory wants a
+        // warp on one row segment (256 contiguous bytes).
+        const int q = warp & 3;                                   // TMEM lane quadrant this warp may read
+        double* tbuf = reinterpret_cast<double*>(sA) + (warp - 2) * (32 * 33);
+        const int row_l = q * 32 + lane;
+        const double sa = (m0 + row_l < g.M) ? g.alpha * g.exa[g.arow0 + m0 + row_l] * (1.0 / 4096.0) : 0.0;
+#pragma unroll 1
+        for (int h = 0; h < OZ_BN / 32; h++) {
+            double acc[32];
+#pragma unroll
+            for (int j = 0; j < 32; j++) acc[j] = 0.0;
+            double w = 1.0;
+#pragma unroll 1
+            for (int c = 0; c < OZ_S; c++) {
+                uint32_t v[32];
+                tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(c * OZ_BN + h * 32), v);
+#pragma unroll
+                for (int j = 0; j < 32; j++) acc[j] = fma(i32_to_f64(v[j]), w, acc[j]);
+                w *= (1.0 / 128.0);
+            }
+#pragma unroll
+            for (int j = 0; j < 32; j++) tbuf[lane * 33 + j] = acc[j] * sa;     // row scale applied here
+            __syncwarp();
+            // now lane = column
+            const int col = n0 + h * 32 + lane;
+            const bool cok = col < g.N;
+            const double sb = cok ? g.exb[g.brow0 + col] : 0.0;
+            // 32 independent coalesced loads in flight, then the dependent stores
+            double cold[32];
+            unsigned okmask = 0;
+#pragma unroll
+            for (int r = 0; r < 32; r++) {
+                const int row = m0 + q * 32 + r;
+                const bool ok = row < g.M && cok && (!g.tri || ((int64_t)col + g.coff <= (int64_t)row + g.roff));
+                okmask |= ok ? (1u << r) : 0u;
+                cold[r] = ok ? g.C[(int64_t)row * g.ldc + col] : 0.0;
+            }
+#pragma unroll
+            for (int r = 0; r < 32; r++)
+                if ((okmask >> r) & 1u) g.C[(int64_t)(m0 + q * 32 + r) * g.ldc + col] = cold[r] + tbuf[r * 33 + lane] * sb;
+            __syncwarp();
+        }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
+}
+
+// ------------------------------------------------------------------------------------------------ host side
+static inline int64_t oz_rows_pad(int64_t rows) { return ((rows + 127) / 128) * 128; }
+
+int64_t oz_slice_buffer_bytes(int64_t rows, int64_t K) { return oz_rows_pad(rows) * K * OZ_S + oz_rows_pad(rows) * (int64_t)sizeof(double); }
+
+// slices rows x K of P into buf (digits) + exponents stored right behind them
+int oz_slice(Ctx* ctx, const double* P, int64_t rows, int64_t K, int64_t ld, void* buf, cudaStream_t st) {
+    if (K % OZ_BK != 0 || (ld & 1) || ((uintptr_t)P & 15)) return BGP_E_ARG;
+    const int64_t rp = oz_rows_pad(rows), nrb = rp / 128;
+    int8_t* dig = reinterpret_cast<int8_t*>(buf);
+    double* ex = reinterpret_cast<double*>(dig + rp * K * OZ_S);
+    oz_slice_kernel<<<(unsigned)(rp / 8), 512, 0, st>>>(P, rows, K, ld, dig, ex, nrb);
+    BGP_LAUNCH_OK(ctx);
+    return 0;
+}
+
+int oz_gemm(Ctx* ctx, const void* bufA, int64_t rowsA_total, int64_t arow0, const void* bufB, int64_t rowsB_total, int64_t brow0,
+            int64_t M, int64_t N, int64_t K, double alpha, double* C, int64_t ldc, int tri, int64_t roff, int64_t coff,
+            cudaStream_t st) {
+    if (M <= 0 || N <= 0) return 0;
+    if (K % OZ_BK != 0 || (arow0 & 127) || (brow0 & 63)) return BGP_E_ARG;
+    const int64_t rpa = oz_rows_pad(rowsA_total), rpb = oz_rows_pad(rowsB_total);
+    OzArgs g;
+    g.sa = reinterpret_cast<const int8_t*>(bufA); g.nrb_a = rpa / 128; g.arow0 = arow0;
+    g.sb = reinterpret_cast<const int8_t*>(bufB); g.nrb_b = rpb / 128; g.brow0 = brow0;
+    g.exa = reinterpret_cast<const double*>(g.sa + rpa * K * OZ_S);
+    g.exb = reinterpret_cast<const double*>(g.sb + rpb * K * OZ_S);
+    g.C = C; g.ldc = ldc; g.M = (int)M; g.N = (int)N; g.K = (int)K; g.alpha = alpha; g.tri = tri; g.roff = roff; g.coff = coff;
+    g.debug_noload = (ctx->gemm_cfg == 7) ? 1 : 0;
+    constexpr int SMEM = OZ_STAGES * (OZ_A_STAGE + OZ_B_STAGE) + 1024 + 256;
+    static thread_local uint64_t attr_done = 0;
+    const uint64_t bit = 1ull << (ctx->device & 63);
+    if (!(attr_done & bit)) {
+        BGP_CUDA_OK(cudaFuncSetAttribute(oz_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
+        attr_done |= bit;
+    }
+    const int tiles_m = (int)((M + OZ_BM - 1) / OZ_BM), tiles_n = (int)((N + OZ_BN - 1) / OZ_BN);
+    oz_mma_kernel<<<tiles_m * tiles_n, 192, SMEM, st>>>(g, tiles_m, tiles_n);
+    BGP_LAUNCH_OK(ctx);
+    return 0;
+}
+
+}  // namespace bgp

@@ -10,6 +10,7 @@ from __future__ import annotations
 
 import ctypes as C
 import math
+import os
 import warnings
 from dataclasses import dataclass, field
 from typing import Optional, Sequence
@@ -130,6 +131,10 @@ class Engine:
         h = C.c_void_p()
         _lib.check(self.L.bgp_ctx_create(self.device.index, C.byref(h)), "bgp_ctx_create")
         self.h = h
+        # fp64-accurate int8/tcgen05 trailing updates (csrc/ozaki.cu) are on by default; BATTGP_OZAKI=0 keeps every
+        # contraction on the FP64 DMMA pipe
+        self.ozaki = False
+        self.set("ozaki", 0 if os.environ.get("BATTGP_OZAKI", "1") == "0" else 1)
 
     def __del__(self):
         try:
@@ -145,6 +150,23 @@ class Engine:
 
     def set(self, key: str, value: int):
         _lib.check(self.L.bgp_ctx_set(self.h, key.encode(), int(value)), f"bgp_ctx_set({key})")
+        if key == "ozaki":
+            self.ozaki = bool(value)
+
+    def _ensure_workspace(self, n: int):
+        """Scratch for the int8/tcgen05 trailing updates: a torch tensor (so empty_cache() can release it), re-used."""
+        if not getattr(self, "ozaki", False):
+            return
+        need = int(self.L.bgp_potrf_workspace_bytes(self.h, n))
+        ws = getattr(self, "_ws", None)
+        if need and (ws is None or ws.numel() < need):
+            self._ws = None
+            self._ws = torch.empty(need, dtype=torch.uint8, device=self.device)
+            _lib.check(self.L.bgp_ctx_set_workspace(self.h, _ptr(self._ws), self._ws.numel()), "bgp_ctx_set_workspace")
+
+    def release_workspace(self):
+        _lib.check(self.L.bgp_ctx_set_workspace(self.h, C.c_void_p(0), 0), "bgp_ctx_set_workspace")
+        self._ws = None
 
     @property
     def launches(self) -> int:
@@ -196,12 +218,25 @@ class Engine:
         _lib.check(rc, "bgp_gemm_nt")
         return C_
 
+    def gemm_nt_i8(self, A: torch.Tensor, B: torch.Tensor, C_: torch.Tensor, alpha=1.0, tri=False, roff=0, coff=0, work=None):
+        """EXPERIMENTAL: C += alpha * A B^T through int8 slicing on tcgen05 (Ozaki scheme)."""
+        M, K = A.shape
+        N = B.shape[0]
+        need = int(self.L.bgp_gemm_nt_i8_work_bytes(M, N, K))
+        if work is None or work.numel() < need:
+            work = torch.empty(need, dtype=torch.uint8, device=self.device)
+        rc = self.L.bgp_gemm_nt_i8(self.h, M, N, K, float(alpha), _ptr(A), self._ld(A), _ptr(B), self._ld(B), _ptr(C_),
+                                   self._ld(C_), 1 if tri else 0, roff, coff, _ptr(work), work.numel(), self._stream())
+        _lib.check(rc, "bgp_gemm_nt_i8")
+        return C_
+
     # ------------------------------------------------------------------ K4
     def potrf(self, A: torch.Tensor):
         """In-place lower Cholesky.  Returns (info, logdet, dinv)."""
         _check_f64_cuda(A, "A", self.device)
         n = A.shape[0]
         dinv = torch.empty(int(self.L.bgp_potrf_dinv_elems(n)), dtype=torch.float64, device=self.device)
+        self._ensure_workspace(n)
         logdet = C.c_double(0.0)
         rc = self.L.bgp_potrf(self.h, _ptr(A), n, self._ld(A), _ptr(dinv), C.byref(logdet), self._stream())
         _lib.check(rc, "bgp_potrf")

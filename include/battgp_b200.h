@@ -69,8 +69,13 @@ int  bgp_version(void);
 const char* bgp_last_error(void);                         /* thread-local text of the last BGP_E_CUDA */
 int  bgp_ctx_create(int device, bgp_ctx** out);           /* creates the panel (high-priority) stream + events */
 void bgp_ctx_destroy(bgp_ctx* ctx);
-/* tuning knobs: "nb" outer panel width (multiple of 128), "lookahead" 0/1. returns 0 or BGP_E_ARG */
+/* tuning knobs: "nb" outer panel width (multiple of 128), "lookahead" 0/1, "ozaki" 0/1 (trailing updates on the
+ * int8 tcgen05 path, fp64-accurate), "gemm_cfg" (probing). returns 0 or BGP_E_ARG */
 int  bgp_ctx_set(bgp_ctx* ctx, const char* key, int value);
+/* Optional scratch for bgp_potrf's int8/tcgen05 trailing updates ("ozaki" knob, csrc/ozaki.cu): the caller (torch)
+ * owns the memory; bgp_potrf uses the path only when at least bgp_potrf_workspace_bytes(ctx, n) bytes are set. */
+int64_t bgp_potrf_workspace_bytes(const bgp_ctx* ctx, int64_t n);
+int  bgp_ctx_set_workspace(bgp_ctx* ctx, void* ptr, int64_t bytes);
 /* counts kernels launched through this context since creation (bench.py's gpu_launches) */
 int64_t bgp_ctx_launches(const bgp_ctx* ctx);
 
@@ -97,6 +102,15 @@ int bgp_cov_diag(bgp_ctx* ctx, const bgp_kernel_spec* spec, const double* X, int
 int bgp_gemm_nt(bgp_ctx* ctx, int64_t M, int64_t N, int64_t K, double alpha,
                 const double* A, int64_t lda, const double* B, int64_t ldb,
                 double beta, double* C, int64_t ldc, int tri, int64_t roff, int64_t coff, void* stream);
+
+/* EXPERIMENTAL: same contraction with C += alpha * A * B^T evaluated by int8 slicing on the tcgen05 tensor cores
+ * (Ozaki scheme, fp64-accurate; csrc/ozaki.cu).  K must be a multiple of 64.  work: device scratch of
+ * bgp_gemm_nt_i8_work_bytes(M, N, K) bytes, 256-byte aligned. */
+int64_t bgp_gemm_nt_i8_work_bytes(int64_t M, int64_t N, int64_t K);
+int bgp_gemm_nt_i8(bgp_ctx* ctx, int64_t M, int64_t N, int64_t K, double alpha,
+                   const double* A, int64_t lda, const double* B, int64_t ldb,
+                   double* C, int64_t ldc, int tri, int64_t roff, int64_t coff,
+                   void* work, int64_t work_bytes, void* stream);
 
 /* ---- K4: Cholesky -------------------------------------------------------------------------------------
  * replaces torch.linalg.cholesky_ex inside GPyTorch's psd_safe_cholesky, reached from ExactGP.__call__

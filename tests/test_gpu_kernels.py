@@ -133,7 +133,7 @@ def test_potrf_matches_lapack(eng, n, nb):
         A = _t(k)
         info, logdet, dinv = eng.potrf(A)
     finally:
-        eng.set("nb", 1024)
+        eng.set("nb", 0)
     assert info == 0
     L = np.tril(A.cpu().numpy())
     # cond(K) ~ 1e6..1e7 here: backward-stable factor => relative Frobenius error ~ cond * eps
@@ -151,6 +151,51 @@ def test_potrf_matches_lapack(eng, n, nb):
         assert np.linalg.norm(got - inv_ref) / np.linalg.norm(inv_ref) < 1e-9
 
 
+@pytest.mark.parametrize("M,N,K,tri", [(128, 64, 64, False), (300, 200, 128, False), (1000, 700, 512, False), (1536, 1536, 1024, True)])
+def test_gemm_nt_i8_ozaki_is_fp64_accurate(eng, M, N, K, tri):
+    """int8-sliced tcgen05 product vs an fp64 reference, with badly scaled rows (per-row exponents)."""
+    g = torch.Generator().manual_seed(M + N + K)
+    A = torch.randn(M, K, generator=g, dtype=torch.float64) * torch.exp(3 * torch.randn(M, 1, generator=g, dtype=torch.float64))
+    B = A if tri else torch.randn(N, K, generator=g, dtype=torch.float64) * torch.exp(3 * torch.randn(N, 1, generator=g, dtype=torch.float64))
+    C0 = torch.randn(M, N, generator=g, dtype=torch.float64)
+    ref = C0 - A @ B.T
+    Ad, Bd, Cd = _t(A.numpy()), (_t(B.numpy()) if not tri else None), _t(C0.numpy())
+    if tri:
+        Bd = Ad
+    eng.gemm_nt_i8(Ad, Bd, Cd, alpha=-1.0, tri=tri)
+    out = Cd.cpu()
+    scale = A.abs().amax(1, keepdim=True) * B.abs().amax(1, keepdim=True).T * K
+    err = (out - ref).abs() / scale
+    if tri:
+        low = torch.tril(torch.ones(M, N, dtype=torch.bool))
+        assert torch.equal(out[~low], C0[~low])
+        err = err[low]
+    # fp64's own worst-case bound is K * 2^-53 ~ 1e-16 in these units; dropped slice pairs add <= 2^-56 * #pairs
+    assert err.max().item() < 4e-16 * 8, err.max().item()
+
+
+@pytest.mark.parametrize("n,nb", [(1300, 256), (2500, 512), (5000, 1024)])
+def test_potrf_with_int8_trailing_updates_matches_lapack(eng, n, nb):
+    k, _ = _spd(n, n)
+    ref = sla.cholesky(k, lower=True)
+    res = {}
+    for oz in (1, 0):
+        eng.set("nb", nb); eng.set("ozaki", oz)
+        try:
+            A = _t(k)
+            info, logdet, _ = eng.potrf(A)
+        finally:
+            eng.set("nb", 0); eng.set("ozaki", 1)
+        assert info == 0
+        L = np.tril(A.cpu().numpy())
+        res[oz] = (np.linalg.norm(L - ref) / np.linalg.norm(ref), np.linalg.norm(L @ L.T - k) / np.linalg.norm(k),
+                   abs(logdet - 2 * np.log(np.diag(ref)).sum()))
+    for oz in (1, 0):
+        assert res[oz][0] < 1e-9 and res[oz][1] < 1e-14 and res[oz][2] < 1e-9 * abs(2 * np.log(np.diag(ref)).sum()), res
+    # the int8 path is as accurate as the DMMA path (same order of magnitude of the forward error)
+    assert res[1][0] < 10 * res[0][0] + 1e-13, res
+
+
 def test_potrf_lookahead_equals_plain_recursion(eng):
     k, _ = _spd(2300, 11)
     A1, A2 = _t(k), _t(k)
@@ -161,7 +206,7 @@ def test_potrf_lookahead_equals_plain_recursion(eng):
         i2, ld2, _ = eng.potrf(A2)
     finally:
         eng.set("lookahead", 1)
-        eng.set("nb", 1024)
+        eng.set("nb", 0)
     assert i1 == 0 and i2 == 0
     L1, L2 = torch.tril(A1), torch.tril(A2)
     assert ((L1 - L2).norm() / L2.norm()).item() < 1e-10

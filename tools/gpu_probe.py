@@ -127,3 +127,60 @@ if "grad" in what:
                           "grad": [float(v) for v in g.cpu()]}), flush=True)
         del K, W, st
         torch.cuda.empty_cache()
+if "syrkone" in what:
+    n, k = 16384, 1024
+    A = torch.randn(n, k, dtype=torch.float64, device=dev); C = torch.zeros(n, n, dtype=torch.float64, device=dev)
+    for _ in range(3): eng.gemm_nt(A, A, C, alpha=-1.0, beta=1.0, tri=True)
+    torch.cuda.synchronize()
+if "i8" in what:
+    torch.manual_seed(0)
+    for (M, N, K, tri) in [(128, 64, 64, False), (128, 64, 128, False), (256, 192, 1024, False), (1000, 700, 512, False), (2048, 2048, 1024, True),
+                           (16384, 16384, 512, True), (16384, 16384, 1024, True), (16384, 16384, 2048, True), (16384, 16384, 4096, True)]:
+        A = torch.randn(M, K, dtype=torch.float64, device=dev) * torch.exp(torch.randn(M, 1, dtype=torch.float64, device=dev) * 3)
+        B = A if tri else torch.randn(N, K, dtype=torch.float64, device=dev) * torch.exp(torch.randn(N, 1, dtype=torch.float64, device=dev) * 3)
+        C0 = torch.randn(M, N, dtype=torch.float64, device=dev)
+        C1 = C0.clone(); C2 = C0.clone()
+        eng.gemm_nt(A, B, C1, alpha=-1.0, beta=1.0, tri=tri)
+        work = torch.empty(int(eng.L.bgp_gemm_nt_i8_work_bytes(M, N, K)), dtype=torch.uint8, device=dev)
+        eng.gemm_nt_i8(A, B, C2, alpha=-1.0, tri=tri, work=work)
+        torch.cuda.synchronize()
+        scale = (A.abs().amax(1, keepdim=True) * B.abs().amax(1, keepdim=True).T) * K
+        err = ((C1 - C2).abs() / scale).max().item()
+        rel = ((C1 - C2).norm() / (C1 - C0).norm()).item()
+        res = {"op": "gemm_nt_i8", "M": M, "N": N, "K": K, "tri": tri, "max_err_over_rowmax_colmax_K": err, "rel_fro_vs_dmma": rel}
+        if M >= 2048:
+            ms = ev(lambda: eng.gemm_nt_i8(A, B, C2, alpha=-1.0, tri=tri, work=work), reps=3)
+            ms_d = ev(lambda: eng.gemm_nt(A, B, C1, alpha=-1.0, beta=1.0, tri=tri), reps=3)
+            fl = (1 if tri else 2) * M * N * K
+            res.update({"ms_i8_incl_slicing": ms, "tflops_equiv": fl / ms * 1e-9, "ms_dmma": ms_d, "tflops_dmma": fl / ms_d * 1e-9})
+            eng.set("gemm_cfg", 7)
+            ms_nl = ev(lambda: eng.gemm_nt_i8(A, B, C2, alpha=-1.0, tri=tri, work=work), reps=3)
+            eng.set("gemm_cfg", 0)
+            res.update({"ms_i8_noload_experiment": ms_nl, "tflops_equiv_noload": fl / ms_nl * 1e-9})
+        print(json.dumps(res), flush=True)
+        del A, B, C0, C1, C2, work
+
+if "ozpotrf" in what:
+    for n in (8192, 16384, 40000):
+        x, y = synth_field_data(n, 0)
+        xd = torch.tensor(x, device=dev); spec = E.battgp_spec()
+        K = E.alloc_matrix(n, n, dev); Kref = E.alloc_matrix(n, n, dev)
+        eng.set("ozaki", 0); eng.set("nb", 1024)
+        eng.cov_build(spec, xd, noise=2.33e-6, symmetric=True, out=Kref)
+        info0, ld0, _ = eng.potrf(Kref)
+        for nb in (1024, 2048):
+            if n <= 2 * nb: continue
+            eng.set("nb", nb); eng.set("ozaki", 1)
+            best = 1e30
+            for r in range(2):
+                eng.cov_build(spec, xd, noise=2.33e-6, symmetric=True, out=K)
+                torch.cuda.synchronize()
+                e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+                e0.record(); info, ld, dinv = eng.potrf(K); e1.record(); torch.cuda.synchronize()
+                best = min(best, e0.elapsed_time(e1))
+            dL = (torch.tril(K) - torch.tril(Kref)).norm() / torch.tril(Kref).norm()
+            print(json.dumps({"op": "potrf_ozaki", "n": n, "nb": nb, "info": info, "ms": best, "tflops_equiv": n ** 3 / 3 / best * 1e-9,
+                              "rel_L_vs_dmma": float(dL), "logdet_diff": ld - ld0}), flush=True)
+        eng.set("ozaki", 0); eng.set("nb", 1024)
+        del K, Kref
+        torch.cuda.empty_cache()
