@@ -332,6 +332,26 @@ int bgp_rowsumsq(bgp_ctx* c, const double* V, int64_t m, int64_t n, int64_t ldv,
     return rowsumsq(ctx, V, m, n, ldv, out, accumulate, (cudaStream_t)stream);
 }
 
+int64_t bgp_oz_slice_bytes(int64_t rows, int64_t K) { return (rows <= 0 || K <= 0) ? 0 : ((oz_slice_buffer_bytes(rows, K) + 255) / 256) * 256; }
+
+int bgp_oz_slice(bgp_ctx* c, const double* P, int64_t rows, int64_t K, int64_t ld, void* buf, int64_t buf_bytes, void* stream) {
+    CTX_OR_FAIL(c);
+    if (rows <= 0) return 0;
+    if (!P || !buf || K <= 0 || K % 64 || ld < K || buf_bytes < oz_slice_buffer_bytes(rows, K) || ((uintptr_t)buf & 255)) return BGP_E_ARG;
+    return oz_slice(ctx, P, rows, K, ld, buf, (cudaStream_t)stream);
+}
+
+int bgp_oz_gemm(bgp_ctx* c, const void* bufA, int64_t rowsA, int64_t arow0, const void* bufB, int64_t rowsB, int64_t brow0,
+                int64_t M, int64_t N, int64_t K, double alpha, double* C, int64_t ldc, int tri, int64_t roff, int64_t coff,
+                void* stream) {
+    CTX_OR_FAIL(c);
+    if (M < 0 || N < 0 || M > INT_MAX || N > INT_MAX) return BGP_E_ARG;
+    if (M == 0 || N == 0) return 0;
+    if (!bufA || !bufB || !C || K <= 0 || K % 64 || ldc < N || arow0 < 0 || brow0 < 0 || arow0 + M > ((rowsA + 127) / 128) * 128 ||
+        brow0 + N > ((rowsB + 127) / 128) * 128) return BGP_E_ARG;
+    return oz_gemm(ctx, bufA, rowsA, arow0, bufB, rowsB, brow0, M, N, K, alpha, C, ldc, tri ? 1 : 0, roff, coff, (cudaStream_t)stream);
+}
+
 int64_t bgp_gemm_nt_i8_work_bytes(int64_t M, int64_t N, int64_t K) {
     return oz_slice_buffer_bytes(M, K) + oz_slice_buffer_bytes(N, K) + 512;
 }

@@ -230,6 +230,21 @@ class Engine:
         _lib.check(rc, "bgp_gemm_nt_i8")
         return C_
 
+    def oz_slice(self, P: torch.Tensor, buf: Optional[torch.Tensor] = None) -> torch.Tensor:
+        rows, K = P.shape
+        need = int(self.L.bgp_oz_slice_bytes(rows, K))
+        if buf is None or buf.numel() < need:
+            buf = torch.empty(need, dtype=torch.uint8, device=self.device)
+        _lib.check(self.L.bgp_oz_slice(self.h, _ptr(P), rows, K, self._ld(P), _ptr(buf), buf.numel(), self._stream()), "bgp_oz_slice")
+        return buf
+
+    def oz_gemm(self, bufA, rowsA, arow0, bufB, rowsB, brow0, C_, K, alpha=-1.0, tri=False, roff=0, coff=0):
+        M, N = C_.shape
+        rc = self.L.bgp_oz_gemm(self.h, _ptr(bufA), rowsA, arow0, _ptr(bufB), rowsB, brow0, M, N, K, float(alpha), _ptr(C_),
+                                self._ld(C_), 1 if tri else 0, roff, coff, self._stream())
+        _lib.check(rc, "bgp_oz_gemm")
+        return C_
+
     # ------------------------------------------------------------------ K4
     def potrf(self, A: torch.Tensor):
         """In-place lower Cholesky.  Returns (info, logdet, dinv)."""

@@ -66,6 +66,16 @@ class CudaOps:
     def gemm_nt(self, A, B, C, alpha, beta, tri=False, roff=0, coff=0):
         self.eng.gemm_nt(A, B, C, alpha=alpha, beta=beta, tri=tri, roff=roff, coff=coff)
 
+    @property
+    def has_oz(self):
+        return self.eng.ozaki
+
+    def oz_slice(self, P, buf):
+        return self.eng.oz_slice(P, buf)
+
+    def oz_gemm(self, buf, rows, arow0, brow0, C, K, alpha, tri, roff, coff):
+        self.eng.oz_gemm(buf, rows, arow0, buf, rows, brow0, C, K, alpha=alpha, tri=tri, roff=roff, coff=coff)
+
     def trsv(self, L, dinv, b, trans):
         self.eng.trsv(L, dinv, b, trans)
 
@@ -176,13 +186,20 @@ class ShardedGP:
                 del recv
             else:
                 panel = send
-            # trailing update of the owned stripes
+            # trailing update of the owned stripes; with the int8/tcgen05 path the gathered panel is sliced ONCE and
+            # every stripe's product re-uses the digit planes
+            use_oz = getattr(ops, "has_oz", False) and nbk % 64 == 0 and len(mine) > 0
+            if use_oz:
+                self._ozbuf = ops.oz_slice(panel, getattr(self, "_ozbuf", None))
             for t, i in enumerate(mine):
                 b0i, ei = self.b0(i), self.e(i)
-                A = panel[(i - k - 1) * NB:(i - k - 1) * NB + self.nbi(i)]
-                B = panel[:ei - ek]
                 C = self.rows[i][:, ek:ei]
-                ops.gemm_nt(A, B, C, -1.0, 1.0, tri=True, roff=b0i, coff=ek)
+                if use_oz:
+                    ops.oz_gemm(self._ozbuf, panel.shape[0], (i - k - 1) * NB, 0, C, nbk, -1.0, True, b0i, ek)
+                else:
+                    A = panel[(i - k - 1) * NB:(i - k - 1) * NB + self.nbi(i)]
+                    B = panel[:ei - ek]
+                    ops.gemm_nt(A, B, C, -1.0, 1.0, tri=True, roff=b0i, coff=ek)
         self._allreduce(logdet)
         self._allreduce(info, dist.ReduceOp.MIN if dist.is_initialized() else None)
         self.logdet = float(logdet.item())
@@ -366,9 +383,7 @@ def bench(args, rank: int, world: int, dev: torch.device):
                 "clocks": clocks, "gpu_launches": int(launches),
                 "e2e": {"value": flops / sec * 1e-9, "unit": "GF/s", "note": "X,y replicated in HBM; host e2e measured on the per_gpu workload",
                         "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 2 * B.M_QUERY * 8},
-                "roofline": {"bound": "tensor", "achieved": (n ** 3 / 3.0) / sec * 1e-12 / world, "peak": B.FP64_DMMA_PEAK_TFLOPS,
-                             "unit": "TFLOP/s per GPU (whole step, not only the factorisation)",
-                             "frac": (n ** 3 / 3.0) / sec * 1e-12 / world / B.FP64_DMMA_PEAK_TFLOPS, "traffic": None}}
+                "roofline": B.step_roofline(n, sec, world, eng.ozaki)}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

@@ -30,10 +30,30 @@ sys.path.insert(0, ROOT)
 M_QUERY = 300
 NOISE = 2.33e-6
 FP64_DMMA_PEAK_TFLOPS = 37.1   # measured on this pool's B200: profiles/fp64_peak_r01.txt (MEASURED_PEAKS.json has no fp64 entry)
+# dram__bytes_read.sum + dram__bytes_write.sum summed over the kernels of one bgp_potrf call, from the committed ncu launch
+# list (profiles/launches_r01_summary.txt, DMMA path: 315 GB) -- N -> bytes
+TRAFFIC_BYTES_PER_POTRF = {40000: 3.15e11}
 
 
 def algorithmic_flops(n: int, m: int = M_QUERY) -> float:
     return n ** 3 / 3.0 + float(n) ** 2 * m + 2.0 * float(n) ** 2
+
+
+def step_roofline(n: int, sec: float, world: int, ozaki: bool) -> dict:
+    """Roofline of a whole sharded step (N^3/3 of N^3/3 + N^2 M + 2 N^2 flop is the factorisation), per GPU."""
+    fp64_equiv = (n ** 3 / 3.0) / sec * 1e-12 / world
+    if not ozaki:
+        return {"bound": "tensor", "achieved": fp64_equiv, "peak": FP64_DMMA_PEAK_TFLOPS, "unit": "TFLOP/s per GPU (whole step)",
+                "frac": fp64_equiv / FP64_DMMA_PEAK_TFLOPS, "traffic": None}
+    try:
+        bf16 = float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["bf16_tflops"])
+        src = "2 x MEASURED_PEAKS.json bf16_tflops"
+    except Exception:
+        bf16, src = 1590.0, "2 x fallback 1.59 PFLOP/s"
+    ach = 36.0 * fp64_equiv
+    return {"bound": "tensor", "achieved": ach, "peak": 2.0 * bf16, "unit": "TOP/s int8 per GPU (whole step; 36 int8 ops per fp64 flop)",
+            "frac": ach / (2.0 * bf16), "peak_source": src, "fp64_equivalent_tflops_per_gpu": fp64_equiv,
+            "fp64_equivalent_over_dmma_peak": fp64_equiv / FP64_DMMA_PEAK_TFLOPS, "traffic": None}
 
 
 class ClockSampler:
@@ -250,23 +270,45 @@ def run_gpu(args, n_gpus: int):
             dist.destroy_process_group()
         return
     pm = statistics.mean(potrf_ms)
-    achieved = n ** 3 / 3.0 / (pm * 1e-3) * 1e-12
+    fp64_equiv = n ** 3 / 3.0 / (pm * 1e-3) * 1e-12
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    bf16_peak = float(peaks.get("bf16_tflops", 1590.0))
+    bf16_src = "MEASURED_PEAKS.json bf16_tflops (burst)" if "bf16_tflops" in peaks else "fallback 1.59 PFLOP/s (B200_PROFILING.md)"
+    if eng.ozaki:
+        # the trailing updates run as 36 exact int8 x int8 -> int32 tcgen05 products per fp64 product (csrc/ozaki.cu);
+        # the int8 tensor rate on sm_100a is 2x the bf16 rate, so the denominator is 2 x the measured bf16 peak
+        int8_ops = 36.0 * n ** 3 / 3.0
+        achieved = int8_ops / (pm * 1e-3) * 1e-12
+        peak = 2.0 * bf16_peak
+        roof = {"bound": "tensor", "kernel": "bgp_potrf: oz_mma_kernel (tcgen05.mma kind::i8 / UTCIMMA, TMEM accumulators, cp.async.bulk "
+                                             "pipeline) trailing updates + DMMA panel/leaf kernels",
+                "achieved": achieved, "peak": peak, "unit": "TOP/s (int8, 36 int8 ops per fp64 flop of the Ozaki scheme)",
+                "frac": achieved / peak, "peak_source": "2 x " + bf16_src + " (no int8 entry; kind::i8 issues at twice the kind::f16 rate)",
+                "fp64_equivalent_tflops": fp64_equiv, "fp64_dmma_peak_tflops": FP64_DMMA_PEAK_TFLOPS,
+                "fp64_equivalent_over_dmma_peak": fp64_equiv / FP64_DMMA_PEAK_TFLOPS,
+                "algorithmic_flop_per_launch": n ** 3 / 3.0, "traffic": TRAFFIC_BYTES_PER_POTRF.get(n)}
+    else:
+        roof = {"bound": "tensor", "kernel": "bgp_potrf (gemm_nt_kernel DMMA.8x8x4 trailing updates + leaf/panel kernels)",
+                "achieved": fp64_equiv, "peak": FP64_DMMA_PEAK_TFLOPS, "unit": "TFLOP/s", "frac": fp64_equiv / FP64_DMMA_PEAK_TFLOPS,
+                "peak_source": "measured FP64 DMMA microbenchmark on this pool (profiles/fp64_peak_r01.txt); "
+                               "MEASURED_PEAKS.json records no fp64 peak (tcgen05 has no f64 kind)",
+                "algorithmic_flop_per_launch": n ** 3 / 3.0, "traffic": TRAFFIC_BYTES_PER_POTRF.get(n)}
     line = {
         "metric": "exact_gp_fit_predict_gflops", "value": value, "unit": "GF/s", "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f64", "data": "synthetic",
         "config": {"workload": workload_name(args, world), "n": n, "m_query": M_QUERY, "kernel": "wiener+rbf_ard",
                    "l2_policy": "inputs_exceed_l2 (K is %.1f GB per GPU, rebuilt every step)" % (8.0 * n * n / 1e9),
-                   "fit_predict_seconds": sec, "potrf_ms": pm},
+                   "fit_predict_seconds": sec, "potrf_ms": pm, "trailing_update_path": "int8_tcgen05_ozaki" if eng.ozaki else "fp64_dmma"},
         "clocks": clocks,
         "e2e": {"value": e2e_value, "unit": "GF/s", "seconds": sec_e2e,
                 "h2d_bytes_per_step": int(xh.numel() + yh.numel() + xqh.numel()) * 8, "d2h_bytes_per_step": 2 * M_QUERY * 8},
         "gpu_launches": int(launches),
-        "roofline": {"bound": "tensor", "kernel": "bgp_potrf (gemm_nt_kernel DMMA.8x8x4 trailing updates + leaf/panel kernels)",
-                     "achieved": achieved, "peak": FP64_DMMA_PEAK_TFLOPS, "unit": "TFLOP/s", "frac": achieved / FP64_DMMA_PEAK_TFLOPS,
-                     "peak_source": "measured FP64 DMMA microbenchmark on this pool (profiles/fp64_peak_r01.txt); "
-                                    "MEASURED_PEAKS.json records no fp64 peak (bf16 tcgen05 has no f64 kind)",
-                     "algorithmic_flop_per_launch": n ** 3 / 3.0, "traffic": None},
+        "roofline": roof,
     }
     if world == 1 and not args.no_cpu_baseline:
         line["cpu_baseline"] = cpu_baseline(args)

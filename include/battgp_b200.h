@@ -112,6 +112,15 @@ int bgp_gemm_nt_i8(bgp_ctx* ctx, int64_t M, int64_t N, int64_t K, double alpha,
                    double* C, int64_t ldc, int tri, int64_t roff, int64_t coff,
                    void* work, int64_t work_bytes, void* stream);
 
+/* The two halves of bgp_gemm_nt_i8, for callers that re-use one sliced panel for many products (sharded trailing update):
+ * bgp_oz_slice: rows x K fp64 (K % 64 == 0) -> 8 int8 digit planes + per-row scales in buf (bgp_oz_slice_bytes, 256-B aligned).
+ * bgp_oz_gemm : C[M,N] += alpha * A B^T with A = rows arow0.. (multiple of 128) of bufA, B = rows brow0.. (multiple of 64) of bufB. */
+int64_t bgp_oz_slice_bytes(int64_t rows, int64_t K);
+int bgp_oz_slice(bgp_ctx* ctx, const double* P, int64_t rows, int64_t K, int64_t ld, void* buf, int64_t buf_bytes, void* stream);
+int bgp_oz_gemm(bgp_ctx* ctx, const void* bufA, int64_t rowsA, int64_t arow0, const void* bufB, int64_t rowsB, int64_t brow0,
+                int64_t M, int64_t N, int64_t K, double alpha, double* C, int64_t ldc, int tri, int64_t roff, int64_t coff,
+                void* stream);
+
 /* ---- K4: Cholesky -------------------------------------------------------------------------------------
  * replaces torch.linalg.cholesky_ex inside GPyTorch's psd_safe_cholesky, reached from ExactGP.__call__
  * (battcellgp_full.py:173, standard_models.py:41) and ExactMarginalLogLikelihood (training.py:40).
