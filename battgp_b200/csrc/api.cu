@@ -25,7 +25,7 @@ int rowsumsq(Ctx*, const double*, int64_t, int64_t, int64_t, double*, int, cudaS
 int64_t oz_slice_buffer_bytes(int64_t rows, int64_t K);
 int oz_slice(Ctx*, const double*, int64_t, int64_t, int64_t, void*, cudaStream_t);
 int oz_gemm(Ctx*, const void*, int64_t, int64_t, const void*, int64_t, int64_t, int64_t, int64_t, int64_t, double, double*,
-            int64_t, int, int64_t, int64_t, cudaStream_t);
+            int64_t, int, int64_t, int64_t, cudaStream_t, int tiles_per_cta = 0);
 int potri(Ctx*, double*, int64_t, int64_t, const double*, double*, int64_t, cudaStream_t);
 int lml_grad(Ctx*, const bgp_kernel_spec*, const double*, int64_t, int64_t, const double*, int64_t, const double*,
              double*, cudaStream_t);
@@ -77,7 +77,7 @@ static int potrf_driver(Ctx* ctx, double* A, int64_t n, int64_t lda, double* din
             if (oz) {
                 // panel k-1 was sliced (rows k0.. of it are rows 0.. of its slice buffer)
                 if ((rc = oz_gemm(ctx, ozbuf[(k - 1) & 1], n - k0, 0, ozbuf[(k - 1) & 1], n - k0, 0, n - k0, nbk, NB, -1.0, Akk, lda,
-                                  1, 0, 0, P))) return rc;
+                                  1, 0, 0, P, ctx->oz_tpc))) return rc;
             } else {
                 const double* Lp = A + k0 * lda + (k0 - NB);     // rows k0.., columns of panel k-1
                 GemmArgs g{Lp, lda, Lp, lda, Akk, lda, (int)(n - k0), (int)nbk, (int)NB, -1.0, 1.0, 1, 0, 0};
@@ -94,7 +94,7 @@ static int potrf_driver(Ctx* ctx, double* A, int64_t n, int64_t lda, double* din
             BGP_CUDA_OK(cudaStreamWaitEvent(mainst, ctx->ev_panel[k % 2], 0));
             if (oz) {
                 if ((rc = oz_gemm(ctx, ozbuf[k & 1], below, NB, ozbuf[k & 1], below, NB, n - t0, n - t0, nbk, -1.0,
-                                  A + t0 * lda + t0, lda, 1, 0, 0, mainst))) return rc;
+                                  A + t0 * lda + t0, lda, 1, 0, 0, mainst, ctx->oz_tpc))) return rc;
             } else {
                 const double* Lt = A + t0 * lda + k0;
                 GemmArgs g{Lt, lda, Lt, lda, A + t0 * lda + t0, lda, (int)(n - t0), (int)(n - t0), (int)nbk, -1.0, 1.0, 1, 0, 0};
@@ -184,6 +184,8 @@ int bgp_ctx_set(bgp_ctx* p, const char* key, int value) {
     }
     if (!strcmp(key, "lookahead")) { c->lookahead = value ? 1 : 0; return 0; }
     if (!strcmp(key, "ozaki")) { c->ozaki = value ? 1 : 0; return 0; }
+    if (!strcmp(key, "oz_cluster")) { if (value != 1 && value != 2 && value != 4) return BGP_E_ARG; c->oz_cluster = value; return 0; }
+    if (!strcmp(key, "oz_tpc")) { if (value < 0 || value > 4096) return BGP_E_ARG; c->oz_tpc = value; return 0; }
     if (!strcmp(key, "gemm_cfg")) { if (value < 0 || value > 7) return BGP_E_ARG; c->gemm_cfg = value; return 0; }
     return BGP_E_ARG;
 }

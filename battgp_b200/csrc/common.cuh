@@ -21,6 +21,8 @@ struct Ctx {
     double* d_scratch = nullptr;            // SCRATCH_BYTES of reduction partials (lml_grad)
     int nb = 0;                             // 0 = automatic (api.cu effective_nb)
     int lookahead = 1;
+    int oz_cluster = 2;                     // CTAs per cluster sharing the A operand by multicast (1, 2 or 4) when fully persistent
+    int oz_tpc = 2;                         // tiles per CTA of the int8 kernel inside bgp_potrf (0 = fully persistent)
     int ozaki = 0;                          // 1: big trailing updates of bgp_potrf go through the int8/tcgen05 path
     void* ws = nullptr;                     // caller-provided scratch (bgp_ctx_set_workspace)
     int64_t ws_bytes = 0;

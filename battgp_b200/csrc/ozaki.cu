@@ -314,6 +314,400 @@ __global__ void __launch_bounds__(192, 1) oz_mma_kernel(OzArgs g, int tiles_m, i
     if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
 }
 
+// ------------------------------------------------------------------------------------------------ persistent variant
+// One CTA per SM loops over the (lower-triangular) tiles.  The three roles run decoupled pipelines:
+//   producer  : keeps the 2-stage operand ring full ACROSS tile boundaries (the next tile's first k-blocks are already in
+//               flight while the current tile is in its epilogue),
+//   MMA issuer: waits for the epilogue to have drained TMEM (tmem_empty), then issues the tile's k-loop,
+//   epilogue  : prefetches the C tile while the MMAs run, drains the 8 accumulators with tcgen05.ld, releases TMEM
+//               (tmem_empty) and only then does the C read-modify-write -- so stores overlap the next tile's MMAs.
+// Removes the per-tile launch / TMEM-alloc / barrier-init / pipeline-fill / C-latency cost of the one-tile-per-CTA form.
+constexpr int OZ_TBUF = 32 * 33;                  // doubles per epilogue warp
+
+__device__ __forceinline__ bool oz_decode_tile(const OzArgs& g, int pid, int tiles_m, int tiles_n, int& m0, int& n0) {
+    constexpr int GROUP = 8;
+    const int per_group = GROUP * tiles_n;
+    const int gid = pid / per_group;
+    const int first_m = gid * GROUP;
+    const int gsize = min(tiles_m - first_m, GROUP);
+    const int tm = first_m + (pid % per_group) % gsize;
+    const int tn = (pid % per_group) / gsize;
+    m0 = tm * OZ_BM;
+    n0 = tn * OZ_BN;
+    return !(g.tri && ((int64_t)n0 + g.coff > (int64_t)m0 + OZ_BM - 1 + g.roff));
+}
+
+__global__ void __launch_bounds__(192, 1) oz_mma_persistent_kernel(OzArgs g, int tiles_m, int tiles_n, int tiles_per_cta) {
+    // this CTA owns raster positions [pid_begin, pid_end); leave before touching TMEM if none of them is a real tile
+    // tiles_per_cta > 0: consecutive raster positions;  tiles_per_cta == 0: grid-stride (fully persistent, one CTA per SM;
+    // concurrently running CTAs then work on neighbouring tiles and share operand panels in L2)
+    const int total = tiles_m * tiles_n;
+    const int pid_step = tiles_per_cta > 0 ? 1 : (int)gridDim.x;
+    const int pid_begin = tiles_per_cta > 0 ? blockIdx.x * tiles_per_cta : (int)blockIdx.x;
+    const int pid_end = tiles_per_cta > 0 ? min(total, pid_begin + tiles_per_cta) : total;
+    {
+        bool any = false;
+        for (int pid = pid_begin; pid < pid_end && !any; pid += pid_step) { int a, b; any = oz_decode_tile(g, pid, tiles_m, tiles_n, a, b); }
+        if (!any) return;
+    }
+    extern __shared__ uint8_t oz_smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(oz_smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint8_t* sA = smem;
+    uint8_t* sB = smem + OZ_STAGES * OZ_A_STAGE;
+    double* tbuf_all = reinterpret_cast<double*>(sB + OZ_STAGES * OZ_B_STAGE);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(tbuf_all + 4 * OZ_TBUF);
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8);
+    const uint32_t full0 = smem_u32(bars), empty0 = smem_u32(bars + OZ_STAGES);
+    const uint32_t tfull = smem_u32(bars + 2 * OZ_STAGES), tempty = smem_u32(bars + 2 * OZ_STAGES + 1);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (warp == 0 && lane == 0) {
+        for (int i = 0; i < OZ_STAGES; i++) { mbar_init(full0 + 8 * i, 1); mbar_init(empty0 + 8 * i, 1); }
+        mbar_init(tfull, 1);
+        mbar_init(tempty, 4);                                   // one arrival per epilogue warp
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem_base = *tmem_slot;
+    const int KB = g.K / OZ_BK;
+
+    if (warp == 0) {
+        uint32_t it = 0;                                        // k-block counter across tiles
+        for (int pid = pid_begin; pid < pid_end; pid += pid_step) {
+            int m0, n0;
+            if (!oz_decode_tile(g, pid, tiles_m, tiles_n, m0, n0)) continue;
+            const int64_t arb = (g.arow0 + m0) >> 7;
+            const int64_t brb = (g.brow0 + n0) >> 7;
+            const int bhalf = (int)(((g.brow0 + n0) >> 6) & 1);
+            for (int kb = 0; kb < KB; kb++, it++) {
+                const int st = it % OZ_STAGES;
+                const uint32_t ph = (it / OZ_STAGES) & 1;
+                mbar_wait(empty0 + 8 * st, ph ^ 1);
+                if (elect_one()) {
+                    mbar_expect_tx(full0 + 8 * st, OZ_A_STAGE + OZ_B_STAGE);
+                    bulk_g2s(smem_u32(sA + st * OZ_A_STAGE), g.sa + ((int64_t)kb * g.nrb_a + arb) * OZ_S * OZ_SLICE_TILE, OZ_A_STAGE,
+                             full0 + 8 * st);
+                    const int8_t* bsrc = g.sb + ((int64_t)kb * g.nrb_b + brb) * OZ_S * OZ_SLICE_TILE + bhalf * 4096;
+#pragma unroll
+                    for (int s = 0; s < OZ_S; s++)
+                        bulk_g2s(smem_u32(sB + st * OZ_B_STAGE + s * 4096), bsrc + (int64_t)s * OZ_SLICE_TILE, 4096, full0 + 8 * st);
+                }
+                __syncwarp();
+            }
+        }
+    } else if (warp == 1) {
+        const uint32_t idesc0 = (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(OZ_BM >> 4) << 24);
+        const uint64_t dzero = oz_desc(0);
+        uint32_t it = 0, tile_it = 0;
+        for (int pid = pid_begin; pid < pid_end; pid += pid_step) {
+            int m0, n0;
+            if (!oz_decode_tile(g, pid, tiles_m, tiles_n, m0, n0)) continue;
+            mbar_wait(tempty, (tile_it & 1) ^ 1);                // epilogue has drained the previous tile's accumulators
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            for (int kb = 0; kb < KB; kb++, it++) {
+                const int st = it % OZ_STAGES;
+                const uint32_t ph = (it / OZ_STAGES) & 1;
+                mbar_wait(full0 + 8 * st, ph);
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                if (elect_one()) {
+                    const uint64_t da0 = dzero + (uint64_t)(smem_u32(sA + st * OZ_A_STAGE) >> 4);
+                    const uint64_t db0 = dzero + (uint64_t)(smem_u32(sB + st * OZ_B_STAGE) >> 4);
+#pragma unroll
+                    for (int ks = 0; ks < OZ_BK / 32; ks++) {
+#pragma unroll
+                        for (int s = 0; s < OZ_S; s++) {
+                            const uint64_t da = da0 + (uint64_t)((s * OZ_SLICE_TILE + ks * 32) >> 4);
+                            const uint32_t acc = (ks > 0 || s > 0) ? 1u : (kb > 0 ? 1u : 0u);
+#pragma unroll
+                            for (int t0 = 0; t0 + s < OZ_S; t0 += 4) {
+                                const int nt = (OZ_S - s - t0) < 4 ? (OZ_S - s - t0) : 4;
+                                const uint64_t db = db0 + (uint64_t)((t0 * 4096 + ks * 32) >> 4);
+                                const uint32_t idesc = idesc0 | ((uint32_t)((nt * OZ_BN) >> 3) << 17);
+                                oz_mma_i8(tmem_base + (uint32_t)(s + t0) * OZ_BN, da, db, idesc, acc);
+                            }
+                        }
+                    }
+                    oz_commit(empty0 + 8 * st);
+                    if (kb == KB - 1) oz_commit(tfull);
+                }
+                __syncwarp();
+            }
+            tile_it++;
+        }
+    } else {
+        const int q = warp & 3;
+        double* tbuf = tbuf_all + (warp - 2) * OZ_TBUF;
+        uint32_t tile_it = 0;
+        for (int pid = pid_begin; pid < pid_end; pid += pid_step) {
+            int m0, n0;
+            if (!oz_decode_tile(g, pid, tiles_m, tiles_n, m0, n0)) continue;
+            const int row_l = q * 32 + lane;
+            const double sa = (m0 + row_l < g.M) ? g.alpha * g.exa[g.arow0 + m0 + row_l] * (1.0 / 4096.0) : 0.0;
+            // prefetch the C values this lane will update (lane = column within a 32-wide half, r = row of the quadrant)
+            double cold[2][32];
+            unsigned okmask[2];
+            double sb[2];
+#pragma unroll
+            for (int h = 0; h < 2; h++) {
+                const int col = n0 + h * 32 + lane;
+                const bool cok = col < g.N;
+                sb[h] = cok ? g.exb[g.brow0 + col] : 0.0;
+                okmask[h] = 0;
+#pragma unroll
+                for (int r = 0; r < 32; r++) {
+                    const int row = m0 + q * 32 + r;
+                    const bool ok = row < g.M && cok && (!g.tri || ((int64_t)col + g.coff <= (int64_t)row + g.roff));
+                    okmask[h] |= ok ? (1u << r) : 0u;
+                    cold[h][r] = ok ? g.C[(int64_t)row * g.ldc + col] : 0.0;
+                }
+            }
+            mbar_wait(tfull, tile_it & 1);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+#pragma unroll
+            for (int h = 0; h < 2; h++) {
+                double acc[32];
+#pragma unroll
+                for (int j = 0; j < 32; j++) acc[j] = 0.0;
+                double w = 1.0;
+#pragma unroll 1
+                for (int c = 0; c < OZ_S; c++) {
+                    uint32_t v[32];
+                    tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(c * OZ_BN + h * 32), v);
+#pragma unroll
+                    for (int j = 0; j < 32; j++) acc[j] = fma(i32_to_f64(v[j]), w, acc[j]);
+                    w *= (1.0 / 128.0);
+                }
+                if (h == 1) {
+                    // all TMEM reads of this warp are done: let the MMA warp start the next tile
+                    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+                    __syncwarp();
+                    if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(tempty) : "memory");
+                }
+#pragma unroll
+                for (int j = 0; j < 32; j++) tbuf[lane * 33 + j] = acc[j] * sa;
+                __syncwarp();
+                const int col = n0 + h * 32 + lane;
+#pragma unroll
+                for (int r = 0; r < 32; r++)
+                    if ((okmask[h] >> r) & 1u) g.C[(int64_t)(m0 + q * 32 + r) * g.ldc + col] = cold[h][r] + tbuf[r * 33 + lane] * sb[h];
+                __syncwarp();
+            }
+            tile_it++;
+        }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
+}
+
+__device__ __forceinline__ void bulk_g2s_mc(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar, uint16_t mask) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1], %2, [%3], %4;"
+                 ::"r"(dst), "l"(src), "r"(bytes), "r"(bar), "h"(mask) : "memory");
+}
+__device__ __forceinline__ void oz_commit_mc(uint32_t bar, uint16_t mask) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+                 ::"r"(bar), "h"(mask) : "memory");
+}
+// group raster: pid -> (tile row, group of CS tile columns); this CTA's own tile is column group*CS + rank.  A group is
+// skipped when its FIRST tile is above the diagonal; the other CTAs of a live group always run (their stores are masked).
+template <int CS>
+__device__ __forceinline__ bool oz_decode_group(const OzArgs& g, int pid, int tiles_m, int tiles_ng, int rank, int& m0, int& n0) {
+    constexpr int GROUP = 8;
+    const int per_group = GROUP * tiles_ng;
+    const int gid = pid / per_group;
+    const int first_m = gid * GROUP;
+    const int gsize = min(tiles_m - first_m, GROUP);
+    const int tm = first_m + (pid % per_group) % gsize;
+    const int tng = (pid % per_group) / gsize;
+    m0 = tm * OZ_BM;
+    n0 = (tng * CS + rank) * OZ_BN;
+    const int nfirst = tng * CS * OZ_BN;
+    return !(g.tri && ((int64_t)nfirst + g.coff > (int64_t)m0 + OZ_BM - 1 + g.roff));
+}
+
+// Cluster variant: CS CTAs (consecutive N tiles of the same tile row) share the A operand.  Each CTA loads 1/CS of the A
+// stage and MULTICASTS it to the whole cluster (cp.async.bulk ... .multicast::cluster), so the L2 -> SM traffic per CTA and
+// stage drops from 96 KB to 32 KB + 64/CS KB -- the one-CTA form is L2-bandwidth bound (~7.5 TB/s) at every K.
+// A stage may only be overwritten once EVERY CTA of the cluster has consumed it: the MMA warps commit with a multicast
+// arrive on the `empty` barriers of all CS CTAs (count = CS).  Fully persistent, grid-stride over groups of CS tiles.
+template <int CS>
+__global__ void __launch_bounds__(192, 1) oz_mma_cluster_kernel(OzArgs g, int tiles_m, int tiles_n, int64_t brb_max) {
+    uint32_t crank;
+    asm volatile("mov.u32 %0, %cluster_ctarank;" : "=r"(crank));
+    const int tiles_ng = (tiles_n + CS - 1) / CS;               // tile groups per tile row
+    const int ncl = gridDim.x / CS, cid = blockIdx.x / CS;
+    const int tiles_per_cta = 0;
+    (void)tiles_per_cta;
+    // this CTA owns raster positions [pid_begin, pid_end); leave before touching TMEM if none of them is a real tile
+    const int total = tiles_m * tiles_ng;
+    const int pid_step = ncl, pid_begin = cid, pid_end = total;
+    // every CTA of a cluster runs the same group sequence (no early exit: peers multicast into this CTA's smem)
+    extern __shared__ uint8_t oz_smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(oz_smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint8_t* sA = smem;
+    uint8_t* sB = smem + OZ_STAGES * OZ_A_STAGE;
+    double* tbuf_all = reinterpret_cast<double*>(sB + OZ_STAGES * OZ_B_STAGE);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(tbuf_all + 4 * OZ_TBUF);
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8);
+    const uint32_t full0 = smem_u32(bars), empty0 = smem_u32(bars + OZ_STAGES);
+    const uint32_t tfull = smem_u32(bars + 2 * OZ_STAGES), tempty = smem_u32(bars + 2 * OZ_STAGES + 1);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (warp == 0 && lane == 0) {
+        for (int i = 0; i < OZ_STAGES; i++) { mbar_init(full0 + 8 * i, 1); mbar_init(empty0 + 8 * i, CS); }
+        mbar_init(tfull, 1);
+        mbar_init(tempty, 4);                                   // one arrival per epilogue warp
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");   // peers' barriers are initialised
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem_base = *tmem_slot;
+    const int KB = g.K / OZ_BK;
+
+    if (warp == 0) {
+        uint32_t it = 0;                                        // k-block counter across tiles
+        for (int pid = pid_begin; pid < pid_end; pid += pid_step) {
+            int m0, n0;
+            if (!oz_decode_group<CS>(g, pid, tiles_m, tiles_ng, (int)crank, m0, n0)) continue;
+            const int64_t arb = (g.arow0 + m0) >> 7;
+            const int64_t brb = min((g.brow0 + n0) >> 7, brb_max);   // tiles past N (odd tile count) read a valid block; stores are masked
+            const int bhalf = (int)(((g.brow0 + n0) >> 6) & 1);
+            for (int kb = 0; kb < KB; kb++, it++) {
+                const int st = it % OZ_STAGES;
+                const uint32_t ph = (it / OZ_STAGES) & 1;
+                mbar_wait(empty0 + 8 * st, ph ^ 1);
+                if (elect_one()) {
+                    mbar_expect_tx(full0 + 8 * st, OZ_A_STAGE + OZ_B_STAGE);
+                    constexpr int APART = OZ_A_STAGE / CS;          // this CTA's share of the A stage, delivered to all CS CTAs
+                    bulk_g2s_mc(smem_u32(sA + st * OZ_A_STAGE + crank * APART),
+                                g.sa + ((int64_t)kb * g.nrb_a + arb) * OZ_S * OZ_SLICE_TILE + (int64_t)crank * APART, APART,
+                                full0 + 8 * st, (uint16_t)((1u << CS) - 1));
+                    const int8_t* bsrc = g.sb + ((int64_t)kb * g.nrb_b + brb) * OZ_S * OZ_SLICE_TILE + bhalf * 4096;
+#pragma unroll
+                    for (int s = 0; s < OZ_S; s++)
+                        bulk_g2s(smem_u32(sB + st * OZ_B_STAGE + s * 4096), bsrc + (int64_t)s * OZ_SLICE_TILE, 4096, full0 + 8 * st);
+                }
+                __syncwarp();
+            }
+        }
+    } else if (warp == 1) {
+        const uint32_t idesc0 = (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(OZ_BM >> 4) << 24);
+        const uint64_t dzero = oz_desc(0);
+        uint32_t it = 0, tile_it = 0;
+        for (int pid = pid_begin; pid < pid_end; pid += pid_step) {
+            int m0, n0;
+            if (!oz_decode_group<CS>(g, pid, tiles_m, tiles_ng, (int)crank, m0, n0)) continue;
+            mbar_wait(tempty, (tile_it & 1) ^ 1);                // epilogue has drained the previous tile's accumulators
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            for (int kb = 0; kb < KB; kb++, it++) {
+                const int st = it % OZ_STAGES;
+                const uint32_t ph = (it / OZ_STAGES) & 1;
+                mbar_wait(full0 + 8 * st, ph);
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                if (elect_one()) {
+                    const uint64_t da0 = dzero + (uint64_t)(smem_u32(sA + st * OZ_A_STAGE) >> 4);
+                    const uint64_t db0 = dzero + (uint64_t)(smem_u32(sB + st * OZ_B_STAGE) >> 4);
+#pragma unroll
+                    for (int ks = 0; ks < OZ_BK / 32; ks++) {
+#pragma unroll
+                        for (int s = 0; s < OZ_S; s++) {
+                            const uint64_t da = da0 + (uint64_t)((s * OZ_SLICE_TILE + ks * 32) >> 4);
+                            const uint32_t acc = (ks > 0 || s > 0) ? 1u : (kb > 0 ? 1u : 0u);
+#pragma unroll
+                            for (int t0 = 0; t0 + s < OZ_S; t0 += 4) {
+                                const int nt = (OZ_S - s - t0) < 4 ? (OZ_S - s - t0) : 4;
+                                const uint64_t db = db0 + (uint64_t)((t0 * 4096 + ks * 32) >> 4);
+                                const uint32_t idesc = idesc0 | ((uint32_t)((nt * OZ_BN) >> 3) << 17);
+                                oz_mma_i8(tmem_base + (uint32_t)(s + t0) * OZ_BN, da, db, idesc, acc);
+                            }
+                        }
+                    }
+                    oz_commit_mc(empty0 + 8 * st, (uint16_t)((1u << CS) - 1));
+                    if (kb == KB - 1) oz_commit(tfull);
+                }
+                __syncwarp();
+            }
+            tile_it++;
+        }
+    } else {
+        const int q = warp & 3;
+        double* tbuf = tbuf_all + (warp - 2) * OZ_TBUF;
+        uint32_t tile_it = 0;
+        for (int pid = pid_begin; pid < pid_end; pid += pid_step) {
+            int m0, n0;
+            if (!oz_decode_group<CS>(g, pid, tiles_m, tiles_ng, (int)crank, m0, n0)) continue;
+            const int row_l = q * 32 + lane;
+            const double sa = (m0 + row_l < g.M) ? g.alpha * g.exa[g.arow0 + m0 + row_l] * (1.0 / 4096.0) : 0.0;
+            // prefetch the C values this lane will update (lane = column within a 32-wide half, r = row of the quadrant)
+            double cold[2][32];
+            unsigned okmask[2];
+            double sb[2];
+#pragma unroll
+            for (int h = 0; h < 2; h++) {
+                const int col = n0 + h * 32 + lane;
+                const bool cok = col < g.N;
+                sb[h] = cok ? g.exb[g.brow0 + col] : 0.0;
+                okmask[h] = 0;
+#pragma unroll
+                for (int r = 0; r < 32; r++) {
+                    const int row = m0 + q * 32 + r;
+                    const bool ok = row < g.M && cok && (!g.tri || ((int64_t)col + g.coff <= (int64_t)row + g.roff));
+                    okmask[h] |= ok ? (1u << r) : 0u;
+                    cold[h][r] = ok ? g.C[(int64_t)row * g.ldc + col] : 0.0;
+                }
+            }
+            mbar_wait(tfull, tile_it & 1);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+#pragma unroll
+            for (int h = 0; h < 2; h++) {
+                double acc[32];
+#pragma unroll
+                for (int j = 0; j < 32; j++) acc[j] = 0.0;
+                double w = 1.0;
+#pragma unroll 1
+                for (int c = 0; c < OZ_S; c++) {
+                    uint32_t v[32];
+                    tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(c * OZ_BN + h * 32), v);
+#pragma unroll
+                    for (int j = 0; j < 32; j++) acc[j] = fma(i32_to_f64(v[j]), w, acc[j]);
+                    w *= (1.0 / 128.0);
+                }
+                if (h == 1) {
+                    // all TMEM reads of this warp are done: let the MMA warp start the next tile
+                    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+                    __syncwarp();
+                    if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(tempty) : "memory");
+                }
+#pragma unroll
+                for (int j = 0; j < 32; j++) tbuf[lane * 33 + j] = acc[j] * sa;
+                __syncwarp();
+                const int col = n0 + h * 32 + lane;
+#pragma unroll
+                for (int r = 0; r < 32; r++)
+                    if ((okmask[h] >> r) & 1u) g.C[(int64_t)(m0 + q * 32 + r) * g.ldc + col] = cold[h][r] + tbuf[r * 33 + lane] * sb[h];
+                __syncwarp();
+            }
+            tile_it++;
+        }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");   // no peer still targets this CTA
+    if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
+}
+
 // ------------------------------------------------------------------------------------------------ host side
 static inline int64_t oz_rows_pad(int64_t rows) { return ((rows + 127) / 128) * 128; }
 
@@ -332,7 +726,7 @@ int oz_slice(Ctx* ctx, const double* P, int64_t rows, int64_t K, int64_t ld, voi
 
 int oz_gemm(Ctx* ctx, const void* bufA, int64_t rowsA_total, int64_t arow0, const void* bufB, int64_t rowsB_total, int64_t brow0,
             int64_t M, int64_t N, int64_t K, double alpha, double* C, int64_t ldc, int tri, int64_t roff, int64_t coff,
-            cudaStream_t st) {
+            cudaStream_t st, int tiles_per_cta) {
     if (M <= 0 || N <= 0) return 0;
     if (K % OZ_BK != 0 || (arow0 & 127) || (brow0 & 63)) return BGP_E_ARG;
     const int64_t rpa = oz_rows_pad(rowsA_total), rpb = oz_rows_pad(rowsB_total);
@@ -343,15 +737,61 @@ int oz_gemm(Ctx* ctx, const void* bufA, int64_t rowsA_total, int64_t arow0, cons
     g.exb = reinterpret_cast<const double*>(g.sb + rpb * K * OZ_S);
     g.C = C; g.ldc = ldc; g.M = (int)M; g.N = (int)N; g.K = (int)K; g.alpha = alpha; g.tri = tri; g.roff = roff; g.coff = coff;
     g.debug_noload = (ctx->gemm_cfg == 7) ? 1 : 0;
-    constexpr int SMEM = OZ_STAGES * (OZ_A_STAGE + OZ_B_STAGE) + 1024 + 256;
-    static thread_local uint64_t attr_done = 0;
-    const uint64_t bit = 1ull << (ctx->device & 63);
-    if (!(attr_done & bit)) {
-        BGP_CUDA_OK(cudaFuncSetAttribute(oz_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
-        attr_done |= bit;
-    }
     const int tiles_m = (int)((M + OZ_BM - 1) / OZ_BM), tiles_n = (int)((N + OZ_BN - 1) / OZ_BN);
-    oz_mma_kernel<<<tiles_m * tiles_n, 192, SMEM, st>>>(g, tiles_m, tiles_n);
+    const uint64_t bit = 1ull << (ctx->device & 63);
+    if (ctx->gemm_cfg == 6) {          // one tile per CTA (kept for comparison / debugging)
+        constexpr int SMEM = OZ_STAGES * (OZ_A_STAGE + OZ_B_STAGE) + 1024 + 256;
+        static thread_local uint64_t attr_done = 0;
+        if (!(attr_done & bit)) {
+            BGP_CUDA_OK(cudaFuncSetAttribute(oz_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
+            attr_done |= bit;
+        }
+        oz_mma_kernel<<<tiles_m * tiles_n, 192, SMEM, st>>>(g, tiles_m, tiles_n);
+    } else {
+        constexpr int SMEM = OZ_STAGES * (OZ_A_STAGE + OZ_B_STAGE) + 4 * OZ_TBUF * (int)sizeof(double) + 1024 + 256;
+        static thread_local uint64_t attr_done = 0;
+        static thread_local int sm_count[64] = {0};
+        if (!(attr_done & bit)) {
+            BGP_CUDA_OK(cudaFuncSetAttribute(oz_mma_persistent_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
+            BGP_CUDA_OK(cudaDeviceGetAttribute(&sm_count[ctx->device & 63], cudaDevAttrMultiProcessorCount, ctx->device));
+            attr_done |= bit;
+        }
+        // tiles per CTA: enough to amortise the prologue and pipeline across tiles, few enough that CTAs keep retiring so
+        // the high-priority panel stream of the look-ahead Cholesky still finds free SMs (a fully persistent grid would
+        // hold every SM until the whole update is done).  tiles_per_cta <= 0 -> fully persistent (one CTA per SM).
+        const int total = tiles_m * tiles_n;
+        const int nsm = sm_count[ctx->device & 63];
+        const int tpc = tiles_per_cta > 0 ? tiles_per_cta : 0;
+        const int cs = (tpc == 0) ? ctx->oz_cluster : 1;
+        if (cs == 2 || cs == 4) {
+            static thread_local uint64_t attr2_done = 0;
+            auto kern = (cs == 2) ? oz_mma_cluster_kernel<2> : oz_mma_cluster_kernel<4>;
+            if (!(attr2_done & bit)) {
+                BGP_CUDA_OK(cudaFuncSetAttribute(oz_mma_cluster_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
+                BGP_CUDA_OK(cudaFuncSetAttribute(oz_mma_cluster_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
+                attr2_done |= bit;
+            }
+            const int tiles_ng = (tiles_n + cs - 1) / cs;
+            const int total_g = tiles_m * tiles_ng;
+            int ncl = nsm / cs;
+            if (ncl > total_g) ncl = total_g;
+            cudaLaunchConfig_t cfg = {};
+            cfg.gridDim = dim3((unsigned)(ncl * cs));
+            cfg.blockDim = dim3(192);
+            cfg.dynamicSmemBytes = SMEM;
+            cfg.stream = st;
+            cudaLaunchAttribute at[1];
+            at[0].id = cudaLaunchAttributeClusterDimension;
+            at[0].val.clusterDim.x = cs; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+            cfg.attrs = at; cfg.numAttrs = 1;
+            const int64_t brb_max = g.nrb_b - 1;
+            BGP_CUDA_OK(cudaLaunchKernelEx(&cfg, kern, g, tiles_m, tiles_n, brb_max));
+            ctx->launches++;
+            return 0;
+        }
+        const int grid = tpc > 0 ? (total + tpc - 1) / tpc : (total < nsm ? total : nsm);
+        oz_mma_persistent_kernel<<<grid, 192, SMEM, st>>>(g, tiles_m, tiles_n, tpc);
+    }
     BGP_LAUNCH_OK(ctx);
     return 0;
 }

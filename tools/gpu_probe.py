@@ -149,14 +149,22 @@ if "i8" in what:
         rel = ((C1 - C2).norm() / (C1 - C0).norm()).item()
         res = {"op": "gemm_nt_i8", "M": M, "N": N, "K": K, "tri": tri, "max_err_over_rowmax_colmax_K": err, "rel_fro_vs_dmma": rel}
         if M >= 2048:
+            C1ref = C0.clone(); eng.gemm_nt(A, B, C1ref, alpha=-1.0, beta=1.0, tri=tri); torch.cuda.synchronize()
             ms = ev(lambda: eng.gemm_nt_i8(A, B, C2, alpha=-1.0, tri=tri, work=work), reps=3)
             ms_d = ev(lambda: eng.gemm_nt(A, B, C1, alpha=-1.0, beta=1.0, tri=tri), reps=3)
             fl = (1 if tri else 2) * M * N * K
             res.update({"ms_i8_incl_slicing": ms, "tflops_equiv": fl / ms * 1e-9, "ms_dmma": ms_d, "tflops_dmma": fl / ms_d * 1e-9})
-            eng.set("gemm_cfg", 7)
-            ms_nl = ev(lambda: eng.gemm_nt_i8(A, B, C2, alpha=-1.0, tri=tri, work=work), reps=3)
-            eng.set("gemm_cfg", 0)
-            res.update({"ms_i8_noload_experiment": ms_nl, "tflops_equiv_noload": fl / ms_nl * 1e-9})
+            for cs in (2, 4):
+                eng.set("oz_cluster", cs)
+                C3 = C0.clone()
+                eng.gemm_nt_i8(A, B, C3, alpha=-1.0, tri=tri, work=work)
+                dd = ((C3 - C2b).abs().max() / C2b.abs().max()).item() if False else 0.0
+                ms_c = ev(lambda: eng.gemm_nt_i8(A, B, C3, alpha=-1.0, tri=tri, work=work), reps=3)
+                C4 = C0.clone(); eng.gemm_nt_i8(A, B, C4, alpha=-1.0, tri=tri, work=work); torch.cuda.synchronize()
+                rel = ((C4 - C1ref).norm() / (C1ref - C0).norm()).item()
+                res.update({f"ms_cluster{cs}": ms_c, f"tflops_cluster{cs}": fl / ms_c * 1e-9, f"rel_cluster{cs}": rel})
+                del C3, C4
+            eng.set("oz_cluster", 1)
         print(json.dumps(res), flush=True)
         del A, B, C0, C1, C2, work
 
@@ -168,9 +176,10 @@ if "ozpotrf" in what:
         eng.set("ozaki", 0); eng.set("nb", 1024)
         eng.cov_build(spec, xd, noise=2.33e-6, symmetric=True, out=Kref)
         info0, ld0, _ = eng.potrf(Kref)
-        for nb in (1024, 2048):
+        for nb, tpc in ((1024, 4), (2048, 4), (1024, 8), (2048, 2), (1024, 1), (2048, 1), (2048, 8)):
             if n <= 2 * nb: continue
-            eng.set("nb", nb); eng.set("ozaki", 1)
+            if n < 40000 and tpc != 4: continue
+            eng.set("nb", nb); eng.set("ozaki", 1); eng.set("oz_tpc", tpc)
             best = 1e30
             for r in range(2):
                 eng.cov_build(spec, xd, noise=2.33e-6, symmetric=True, out=K)
@@ -179,8 +188,8 @@ if "ozpotrf" in what:
                 e0.record(); info, ld, dinv = eng.potrf(K); e1.record(); torch.cuda.synchronize()
                 best = min(best, e0.elapsed_time(e1))
             dL = (torch.tril(K) - torch.tril(Kref)).norm() / torch.tril(Kref).norm()
-            print(json.dumps({"op": "potrf_ozaki", "n": n, "nb": nb, "info": info, "ms": best, "tflops_equiv": n ** 3 / 3 / best * 1e-9,
+            print(json.dumps({"op": "potrf_ozaki", "n": n, "nb": nb, "tpc": tpc, "info": info, "ms": best, "tflops_equiv": n ** 3 / 3 / best * 1e-9,
                               "rel_L_vs_dmma": float(dL), "logdet_diff": ld - ld0}), flush=True)
-        eng.set("ozaki", 0); eng.set("nb", 1024)
+        eng.set("ozaki", 1); eng.set("nb", 0); eng.set("oz_tpc", 4)
         del K, Kref
         torch.cuda.empty_cache()
