@@ -44,6 +44,11 @@ struct DeviceGuard {
     ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
 };
 
+// scratch for the int8 path of the panel TRSM: X1 [n - nb, nb/2] and L21 [nb/2, nb/2] digit planes
+static inline int64_t potrf_trsm_scratch_bytes(int64_t n, int64_t nb) {
+    return ((oz_slice_buffer_bytes(n - nb, nb / 2) + 255) / 256) * 256 + ((oz_slice_buffer_bytes(nb / 2, nb / 2) + 255) / 256) * 256;
+}
+
 // panel width: "nb" knob, or (nb == 0) automatic -- wide panels amortise the fixed per-tile cost of the int8 path
 static inline int64_t effective_nb(const Ctx* ctx, int64_t n) {
     if (ctx->nb > 0) return ctx->nb;
@@ -61,6 +66,13 @@ static int potrf_driver(Ctx* ctx, double* A, int64_t n, int64_t lda, double* din
     const bool oz = ctx->ozaki && ctx->ws && (NB % 64 == 0) && ((lda & 1) == 0) && (((uintptr_t)A & 15) == 0) &&
                     (((uintptr_t)ctx->ws & 255) == 0) && ctx->ws_bytes >= 2 * ozbytes;
     void* ozbuf[2] = {ctx->ws, reinterpret_cast<char*>(ctx->ws) + ozbytes};
+    // the panel TRSM (stream P) gets its own scratch behind the two panel buffers
+    struct TrsmScratch {
+        Ctx* c;
+        TrsmScratch(Ctx* c_, void* p, int64_t b) : c(c_) { c->ws_trsm = p; c->ws_trsm_bytes = b; }
+        ~TrsmScratch() { c->ws_trsm = nullptr; c->ws_trsm_bytes = 0; }
+    } trsm_scratch(ctx, (oz && ctx->ws_bytes > 2 * ozbytes) ? reinterpret_cast<char*>(ctx->ws) + 2 * ozbytes : nullptr,
+                   (oz && ctx->ws_bytes > 2 * ozbytes) ? ctx->ws_bytes - 2 * ozbytes : 0);
     BGP_CUDA_OK(cudaEventRecord(ctx->ev_fork, mainst));
     BGP_CUDA_OK(cudaStreamWaitEvent(P, ctx->ev_fork, 0));
     const int64_t npanels = (n + NB - 1) / NB;
@@ -195,7 +207,7 @@ int64_t bgp_potrf_workspace_bytes(const bgp_ctx* p, int64_t n) {
     const Ctx* c = reinterpret_cast<const Ctx*>(p);
     const int64_t nb = effective_nb(c, n);
     if (n <= 2 * nb) return 0;
-    return 2 * (((oz_slice_buffer_bytes(n - nb, nb) + 255) / 256) * 256);
+    return 2 * (((oz_slice_buffer_bytes(n - nb, nb) + 255) / 256) * 256) + potrf_trsm_scratch_bytes(n, nb);
 }
 
 int bgp_ctx_set_workspace(bgp_ctx* p, void* ptr, int64_t bytes) {

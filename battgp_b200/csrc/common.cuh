@@ -26,6 +26,8 @@ struct Ctx {
     int ozaki = 0;                          // 1: big trailing updates of bgp_potrf go through the int8/tcgen05 path
     void* ws = nullptr;                     // caller-provided scratch (bgp_ctx_set_workspace)
     int64_t ws_bytes = 0;
+    void* ws_trsm = nullptr;                // tail of ws used by the TRSM updates (set by bgp_potrf for its panels)
+    int64_t ws_trsm_bytes = 0;
     int gemm_cfg = 0;                       // 0 = default big-tile config, else forced variant (probing)
     int64_t launches = 0;
 };

@@ -205,6 +205,28 @@ static int launch_leaf(Ctx* ctx, double* A, int64_t lda, int n, double* dinv, in
     return 0;
 }
 
+int64_t oz_slice_buffer_bytes(int64_t rows, int64_t K);
+int oz_slice(Ctx*, const double*, int64_t, int64_t, int64_t, void*, cudaStream_t);
+int oz_gemm(Ctx*, const void*, int64_t, int64_t, const void*, int64_t, int64_t, int64_t, int64_t, int64_t, double, double*,
+            int64_t, int, int64_t, int64_t, cudaStream_t, int tiles_per_cta);
+
+// C[M,N] -= A[M,K] B[N,K]^T on the int8/tcgen05 path if it is enabled, worth it, and the scratch region [ws_trsm, +bytes)
+// of the context workspace can hold the digit planes of both operands.  Returns 1 if done, 0 if the caller must use DMMA.
+static int oz_try_update(Ctx* ctx, const double* A, int64_t lda, int64_t M, const double* B, int64_t ldb, int64_t N, int64_t K,
+                         double* C, int64_t ldc, cudaStream_t st, int* rc) {
+    *rc = 0;
+    if (!ctx->ozaki || !ctx->ws_trsm || K < 512 || (K % 64) || M < 1024 || N < 256) return 0;
+    if ((lda | ldb) & 1 || (((uintptr_t)A | (uintptr_t)B) & 15)) return 0;
+    const int64_t ba = ((oz_slice_buffer_bytes(M, K) + 255) / 256) * 256, bb = ((oz_slice_buffer_bytes(N, K) + 255) / 256) * 256;
+    if (ba + bb > ctx->ws_trsm_bytes) return 0;
+    char* wa = reinterpret_cast<char*>(ctx->ws_trsm);
+    char* wb = wa + ba;
+    if ((*rc = oz_slice(ctx, A, M, K, lda, wa, st))) return 1;
+    if ((*rc = oz_slice(ctx, B, N, K, ldb, wb, st))) return 1;
+    *rc = oz_gemm(ctx, wa, M, 0, wb, N, 0, M, N, K, -1.0, C, ldc, 0, 0, 0, st, ctx->oz_tpc);
+    return 1;
+}
+
 static inline int64_t split_point(int64_t n) {
     // largest multiple of LEAF that is >= n/2 and < n
     int64_t h = ((n / 2 + LEAF - 1) / LEAF) * LEAF;
@@ -225,8 +247,10 @@ int trsm_rlt_rec(Ctx* ctx, const double* L, int64_t n, int64_t ldl, const double
     const int64_t n1 = split_point(n), n2 = n - n1;
     int rc = trsm_rlt_rec(ctx, L, n1, ldl, dinv, X, m, ldx, st);
     if (rc) return rc;
-    GemmArgs g{X, ldx, L + n1 * ldl, ldl, X + n1, ldx, (int)m, (int)n2, (int)n1, -1.0, 1.0, 0, 0, 0};
-    rc = gemm_nt(ctx, g, st);
+    if (!oz_try_update(ctx, X, ldx, m, L + n1 * ldl, ldl, n2, n1, X + n1, ldx, st, &rc)) {
+        GemmArgs g{X, ldx, L + n1 * ldl, ldl, X + n1, ldx, (int)m, (int)n2, (int)n1, -1.0, 1.0, 0, 0, 0};
+        rc = gemm_nt(ctx, g, st);
+    }
     if (rc) return rc;
     return trsm_rlt_rec(ctx, L + n1 * ldl + n1, n2, ldl, dinv + (n1 / LEAF) * (int64_t)LEAF * LEAF, X + n1, m, ldx, st);
 }

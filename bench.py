@@ -31,8 +31,8 @@ M_QUERY = 300
 NOISE = 2.33e-6
 FP64_DMMA_PEAK_TFLOPS = 37.1   # measured on this pool's B200: profiles/fp64_peak_r01.txt (MEASURED_PEAKS.json has no fp64 entry)
 # dram__bytes_read.sum + dram__bytes_write.sum summed over the kernels of one bgp_potrf call, from the committed ncu launch
-# list (profiles/launches_r01_summary.txt, DMMA path: 315 GB) -- N -> bytes
-TRAFFIC_BYTES_PER_POTRF = {40000: 3.15e11}
+# lists (profiles/launches_r01_ozaki_summary.txt: int8 path 275 GB; launches_r01_summary.txt: DMMA-only path 315 GB) -- N -> bytes
+TRAFFIC_BYTES_PER_POTRF = {40000: 2.75e11}
 
 
 def algorithmic_flops(n: int, m: int = M_QUERY) -> float:

@@ -174,7 +174,7 @@ def test_gemm_nt_i8_ozaki_is_fp64_accurate(eng, M, N, K, tri):
     assert err.max().item() < 4e-16 * 8, err.max().item()
 
 
-@pytest.mark.parametrize("n,nb", [(1300, 256), (2500, 512), (5000, 1024)])
+@pytest.mark.parametrize("n,nb", [(1300, 256), (2500, 512), (4321, 512), (5000, 1024), (6200, 2048)])
 def test_potrf_with_int8_trailing_updates_matches_lapack(eng, n, nb):
     k, _ = _spd(n, n)
     ref = sla.cholesky(k, lower=True)

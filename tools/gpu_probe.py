@@ -193,3 +193,9 @@ if "ozpotrf" in what:
         eng.set("ozaki", 1); eng.set("nb", 0); eng.set("oz_tpc", 4)
         del K, Kref
         torch.cuda.empty_cache()
+if "ozone" in what:
+    n, k = 16384, 2048
+    A = torch.randn(n, k, dtype=torch.float64, device=dev); C = torch.zeros(n, n, dtype=torch.float64, device=dev)
+    work = torch.empty(int(eng.L.bgp_gemm_nt_i8_work_bytes(n, n, k)), dtype=torch.uint8, device=dev)
+    for _ in range(3): eng.gemm_nt_i8(A, A, C, alpha=-1.0, tri=True, work=work)
+    torch.cuda.synchronize()
