@@ -64,6 +64,9 @@ int gemm_nt(Ctx* ctx, const GemmArgs& g, cudaStream_t st);
 int gemm_nt_cfg(Ctx* ctx, const GemmArgs& g, int cfg, cudaStream_t st);
 
 // ---- potrf.cu
+int oz_gemm_kchunked(Ctx* ctx, const double* A, int64_t lda, int64_t M, const double* B, int64_t ldb, int64_t N, int64_t K,
+                     double alpha, double* C, int64_t ldc, int tri, bool a_upper, bool same_ab, cudaStream_t st, int tiles_per_cta,
+                     int* rc);
 int potrf_rec(Ctx* ctx, double* A, int64_t n, int64_t lda, double* dinv, int64_t gofs, cudaStream_t st);
 int trsm_rlt_rec(Ctx* ctx, const double* L, int64_t n, int64_t ldl, const double* dinv, double* X, int64_t m,
                  int64_t ldx, cudaStream_t st);

@@ -37,9 +37,13 @@ static int trtri_u_rec(Ctx* ctx, const double* L, int64_t n, int64_t ldl, const 
     const int64_t n2 = n - n1;
     int rc = trtri_u_rec(ctx, L, n1, ldl, dinv, Z, ldz, st);
     if (rc) return rc;
-    // Z12 = -Z11 * L21^T   (Z11 upper-triangular: skip k < row)
-    GemmArgs g{Z, ldz, L + n1 * ldl, ldl, Z + n1, ldz, (int)n1, (int)n2, (int)n1, -1.0, 0.0, 0, 0, 0, 1, 0};
-    if ((rc = gemm_nt(ctx, g, st))) return rc;
+    // Z12 = -Z11 * L21^T   (Z11 upper-triangular: skip k < row).  Z12 is still zero (memset in potri), so the int8 path
+    // can accumulate into it chunk by chunk.
+    if (!oz_gemm_kchunked(ctx, Z, ldz, n1, L + n1 * ldl, ldl, n2, n1, -1.0, Z + n1, ldz, 0, true, false, st, 0, &rc)) {
+        GemmArgs g{Z, ldz, L + n1 * ldl, ldl, Z + n1, ldz, (int)n1, (int)n2, (int)n1, -1.0, 0.0, 0, 0, 0, 1, 0};
+        rc = gemm_nt(ctx, g, st);
+    }
+    if (rc) return rc;
     // Z12 <- Z12 * L22^-T
     const double* dinv2 = dinv + (n1 / LEAF) * (int64_t)LEAF * LEAF;
     if ((rc = trsm_rlt_rec(ctx, L + n1 * ldl + n1, n2, ldl, dinv2, Z + n1, n1, ldz, st))) return rc;
@@ -48,11 +52,33 @@ static int trtri_u_rec(Ctx* ctx, const double* L, int64_t n, int64_t ldl, const 
 
 int potri(Ctx* ctx, double* L, int64_t n, int64_t ldl, const double* dinv, double* work, int64_t ldw, cudaStream_t st) {
     BGP_CUDA_OK(cudaMemset2DAsync(work, ldw * sizeof(double), 0, n * sizeof(double), n, st));
+    // the int8 path (if enabled) slices into the context workspace; everything runs on one stream, so the chunked
+    // products and the TRSM updates can share the whole region
+    struct Scratch {
+        Ctx* c; void* p0; int64_t b0;
+        explicit Scratch(Ctx* c_) : c(c_), p0(c_->ws_trsm), b0(c_->ws_trsm_bytes) { c->ws_trsm = c->ws; c->ws_trsm_bytes = c->ws_bytes; }
+        ~Scratch() { c->ws_trsm = p0; c->ws_trsm_bytes = b0; }
+    } scratch(ctx);
+    const int tpc_saved = ctx->oz_tpc;
+    ctx->oz_tpc = 0;                              // nothing runs concurrently here: fully persistent int8 kernels
     int rc = trtri_u_rec(ctx, L, n, ldl, dinv, work, ldw, st);
-    if (rc) return rc;
-    // Kinv(lower) = Z Z^T, Z upper: contributions only from k >= row
-    GemmArgs g{work, ldw, work, ldw, L, ldl, (int)n, (int)n, (int)n, 1.0, 0.0, 1, 0, 0, 1, 0};
-    return gemm_nt(ctx, g, st);
+    if (!rc) {
+        // Kinv(lower) = Z Z^T, Z upper: contributions only from k >= row
+        int rc2 = 0;
+        // the int8 path accumulates: clear the factor first (it is no longer needed once Z = L^-T exists)
+        bool done = false;
+        if (ctx->ozaki && ctx->ws && n >= 4096) {
+            cudaError_t e = cudaMemset2DAsync(L, ldl * sizeof(double), 0, n * sizeof(double), n, st);
+            if (e != cudaSuccess) { set_error("cudaMemset2DAsync", e); rc = BGP_E_CUDA; }
+            else if (oz_gemm_kchunked(ctx, work, ldw, n, work, ldw, n, n, 1.0, L, ldl, 1, true, true, st, 0, &rc2)) { done = true; rc = rc2; }
+        }
+        if (!rc && !done) {
+            GemmArgs g{work, ldw, work, ldw, L, ldl, (int)n, (int)n, (int)n, 1.0, 0.0, 1, 0, 0, 1, 0};
+            rc = gemm_nt(ctx, g, st);
+        }
+    }
+    ctx->oz_tpc = tpc_saved;
+    return rc;
 }
 
 // ------------------------------------------------------------------------------------------------ lml_grad

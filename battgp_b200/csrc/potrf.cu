@@ -210,21 +210,46 @@ int oz_slice(Ctx*, const double*, int64_t, int64_t, int64_t, void*, cudaStream_t
 int oz_gemm(Ctx*, const void*, int64_t, int64_t, const void*, int64_t, int64_t, int64_t, int64_t, int64_t, double, double*,
             int64_t, int, int64_t, int64_t, cudaStream_t, int tiles_per_cta);
 
-// C[M,N] -= A[M,K] B[N,K]^T on the int8/tcgen05 path if it is enabled, worth it, and the scratch region [ws_trsm, +bytes)
-// of the context workspace can hold the digit planes of both operands.  Returns 1 if done, 0 if the caller must use DMMA.
+// C[M,N] += alpha * A[M,K] B[N,K]^T on the int8/tcgen05 path, K processed in chunks so that the digit planes of both
+// operands fit the scratch region [ws_trsm, +ws_trsm_bytes) of the context.  Returns 1 if the product was issued (or
+// failed: *rc), 0 if the caller must use the DMMA kernel (path disabled, too small to pay off, misaligned, no scratch).
+//   a_upper : A[i][k] == 0 for k < i  (upper-triangular operand: rows beyond a chunk's last column contribute nothing)
+//   same_ab : B is A (SYRK): sliced once, N follows the row restriction
+int oz_gemm_kchunked(Ctx* ctx, const double* A, int64_t lda, int64_t M, const double* B, int64_t ldb, int64_t N, int64_t K,
+                     double alpha, double* C, int64_t ldc, int tri, bool a_upper, bool same_ab, cudaStream_t st, int tiles_per_cta,
+                     int* rc) {
+    *rc = 0;
+    if (!ctx->ozaki || !ctx->ws_trsm || K < 512 || M < 1024 || N < 256) return 0;
+    if ((lda | ldb) & 1 || (((uintptr_t)A | (uintptr_t)B) & 15)) return 0;
+    const int64_t Kmain = (K / 64) * 64;
+    int64_t KC = 2048;
+    if (KC > Kmain) KC = Kmain;
+    auto need = [&](int64_t kc) {
+        return ((oz_slice_buffer_bytes(M, kc) + 255) / 256) * 256 + (same_ab ? 0 : ((oz_slice_buffer_bytes(N, kc) + 255) / 256) * 256);
+    };
+    while (KC > 512 && need(KC) > ctx->ws_trsm_bytes) KC /= 2;
+    if (need(KC) > ctx->ws_trsm_bytes) return 0;
+    char* wa = reinterpret_cast<char*>(ctx->ws_trsm);
+    char* wb = wa + ((oz_slice_buffer_bytes(M, KC) + 255) / 256) * 256;
+    for (int64_t kc = 0; kc < Kmain; kc += KC) {
+        const int64_t kw = (Kmain - kc < KC) ? Kmain - kc : KC;
+        const int64_t m_eff = a_upper ? ((kc + kw < M) ? kc + kw : M) : M;
+        const int64_t n_eff = same_ab ? m_eff : N;
+        if ((*rc = oz_slice(ctx, A + kc, m_eff, kw, lda, wa, st))) return 1;
+        if (!same_ab && (*rc = oz_slice(ctx, B + kc, N, kw, ldb, wb, st))) return 1;
+        if ((*rc = oz_gemm(ctx, wa, m_eff, 0, same_ab ? wa : wb, n_eff, 0, m_eff, n_eff, kw, alpha, C, ldc, tri, 0, 0, st, tiles_per_cta)))
+            return 1;
+    }
+    if (Kmain < K) {      // ragged tail of K (< 64 columns) on the DMMA kernel
+        GemmArgs g{A + Kmain, lda, B + Kmain, ldb, C, ldc, (int)M, (int)N, (int)(K - Kmain), alpha, 1.0, tri, 0, 0};
+        *rc = gemm_nt(ctx, g, st);
+    }
+    return 1;
+}
+
 static int oz_try_update(Ctx* ctx, const double* A, int64_t lda, int64_t M, const double* B, int64_t ldb, int64_t N, int64_t K,
                          double* C, int64_t ldc, cudaStream_t st, int* rc) {
-    *rc = 0;
-    if (!ctx->ozaki || !ctx->ws_trsm || K < 512 || (K % 64) || M < 1024 || N < 256) return 0;
-    if ((lda | ldb) & 1 || (((uintptr_t)A | (uintptr_t)B) & 15)) return 0;
-    const int64_t ba = ((oz_slice_buffer_bytes(M, K) + 255) / 256) * 256, bb = ((oz_slice_buffer_bytes(N, K) + 255) / 256) * 256;
-    if (ba + bb > ctx->ws_trsm_bytes) return 0;
-    char* wa = reinterpret_cast<char*>(ctx->ws_trsm);
-    char* wb = wa + ba;
-    if ((*rc = oz_slice(ctx, A, M, K, lda, wa, st))) return 1;
-    if ((*rc = oz_slice(ctx, B, N, K, ldb, wb, st))) return 1;
-    *rc = oz_gemm(ctx, wa, M, 0, wb, N, 0, M, N, K, -1.0, C, ldc, 0, 0, 0, st, ctx->oz_tpc);
-    return 1;
+    return oz_gemm_kchunked(ctx, A, lda, M, B, ldb, N, K, -1.0, C, ldc, 0, false, false, st, ctx->oz_tpc, rc);
 }
 
 static inline int64_t split_point(int64_t n) {

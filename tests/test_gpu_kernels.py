@@ -258,7 +258,7 @@ def test_trsm_rlt(eng, n, m):
 
 
 # ----------------------------------------------------------------------------------------------- gradient pass
-@pytest.mark.parametrize("n", [100, 129, 700, 1500])
+@pytest.mark.parametrize("n", [100, 129, 700, 1500, 4500, 6200])
 def test_potri(eng, n):
     k, _ = _spd(n, 300 + n)
     A = _t(k)
@@ -268,8 +268,8 @@ def test_potri(eng, n):
     kinv = np.tril(A.cpu().numpy())
     kinv = kinv + np.tril(kinv, -1).T
     ref = np.linalg.inv(k)
-    assert np.linalg.norm(kinv - ref) / np.linalg.norm(ref) < 1e-7       # cond(K) ~ 1e6-1e7
-    assert np.linalg.norm(kinv @ k - np.eye(n)) / math.sqrt(n) < 1e-7
+    assert np.linalg.norm(kinv - ref) / np.linalg.norm(ref) < 3e-7       # cond(K) ~ 1e6-1e7 (n >= 4096: int8 path)
+    assert np.linalg.norm(kinv @ k - np.eye(n)) / math.sqrt(n) < 3e-7
 
 
 @pytest.mark.parametrize("name", ["battgp", "rbf_iso", "matern_periodic"])
