@@ -30,6 +30,7 @@ int potri(Ctx*, double*, int64_t, int64_t, const double*, double*, int64_t, cuda
 int lml_grad(Ctx*, const bgp_kernel_spec*, const double*, int64_t, int64_t, const double*, int64_t, const double*,
              double*, cudaStream_t);
 
+void leaf_clk_read(long long* out);
 __global__ void init_scalars_kernel(int32_t* info, double* scal) {
     if (threadIdx.x == 0) { *info = INT_MAX; scal[0] = 0.0; }
 }
@@ -133,6 +134,7 @@ using namespace bgp;
 extern "C" {
 
 int bgp_version(void) { return BGP_VERSION; }
+void bgp_debug_leaf_clk(long long* out) { bgp::leaf_clk_read(out); }
 const char* bgp_last_error(void) { return g_err; }
 
 int bgp_grad_slots(const bgp_kernel_spec* s) {

@@ -24,32 +24,41 @@ __device__ __forceinline__ void dmma_leaf(double& c0, double& c1, double a, doub
 }
 __device__ __forceinline__ double shfl_d(double v, int src) { return __shfl_sync(0xffffffffu, v, src); }
 
-// One warp, lane i = row i of the 32x32 diagonal block at D (pitch SP).  In-place lower Cholesky held in registers
-// (column broadcasts by shuffle), then the inverse of the factor, one column per lane, into X (pitch BP, zeros above
-// the diagonal).  Returns sum(log d_j); *bad = first failing local column + 1 (0 = none).
-__device__ __forceinline__ double warp_potrf32_inv(double* D, double* X, int lane, int* bad) {
+// One warp, lane i = row i of the 32x32 diagonal block at D (pitch SP): in-place lower Cholesky held in registers (column
+// broadcasts by shuffle).  Writes the factor back to D (zeros above the diagonal) and 1/L_jj to rdiag[0..31].
+// Returns sum_j log d_j (each lane evaluates ONE log, then a warp reduction); *bad = first failing local column + 1.
+__device__ __forceinline__ double warp_potrf32(double* D, double* rdiag, double* colbuf, int lane, int* bad) {
     double a[32];
 #pragma unroll
     for (int k = 0; k < 32; k++) a[k] = (k <= lane) ? D[lane * SP + k] : 0.0;
-    double logsum = 0.0, my_rdiag = 1.0;
+    double my_d = 1.0;
     int fail = 0;
 #pragma unroll
     for (int j = 0; j < 32; j++) {
         const double d = shfl_d(a[j], j);
         if (!(d > 0.0) && fail == 0) fail = j + 1;
-        logsum += log(d);
-        const double r = sqrt(d), rinv = 1.0 / r;
-        const double l = (lane == j) ? r : a[j] * rinv;
+        const double rinv = rsqrt(d);
+        const double l = (lane == j) ? d * rinv : a[j] * rinv;
         a[j] = l;
-        if (lane == j) my_rdiag = rinv;
+        if (lane == j) { my_d = d; rdiag[j] = rinv; }
+        // broadcast the column through shared memory: every lane then reads l_k with one (conflict-free, broadcast) LDS.64
+        colbuf[(j & 1) * 32 + lane] = l;
+        __syncwarp();
 #pragma unroll
-        for (int k = j + 1; k < 32; k++) a[k] = fma(-l, shfl_d(l, k), a[k]);
+        for (int k = j + 1; k < 32; k++) a[k] = fma(-l, colbuf[(j & 1) * 32 + k], a[k]);
     }
     *bad = fail;
 #pragma unroll
     for (int k = 0; k < 32; k++) D[lane * SP + k] = (k <= lane) ? a[k] : 0.0;
-    __syncwarp();
-    // inverse: lane c owns column c;  x_i = (delta_ic - sum_{k<i} L_ik x_k) / L_ii   (x_k = 0 for k < c falls out)
+    double lg = log(my_d);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) lg += __shfl_xor_sync(0xffffffffu, lg, o);
+    return lg;
+}
+
+// One warp: X (pitch BP, zeros above the diagonal) = inverse of the 32x32 lower-triangular factor at D, one column per lane:
+//   x_i = (delta_ic - sum_{k<i} L_ik x_k) / L_ii   (x_k = 0 for k < c falls out)
+__device__ __forceinline__ void warp_trtri32(const double* D, const double* rdiag, double* X, int lane) {
     double x[32];
 #pragma unroll
     for (int i = 0; i < 32; i++) {
@@ -59,63 +68,104 @@ __device__ __forceinline__ double warp_potrf32_inv(double* D, double* X, int lan
             s0 = fma(-D[i * SP + k], x[k], s0);
             if (k + 1 < i) s1 = fma(-D[i * SP + k + 1], x[k + 1], s1);
         }
-        x[i] = (s0 + s1) * shfl_d(my_rdiag, i);
+        x[i] = (s0 + s1) * rdiag[i];
     }
 #pragma unroll
     for (int i = 0; i < 32; i++) X[i * BP + lane] = (i >= lane) ? x[i] : 0.0;
-    return logsum;
 }
 
-// One CTA (8 warps): S = lower(A[0:n,0:n]) (identity-padded to 128); S <- chol(S) by 32-wide panels -- diagonal block
-// factored + inverted by one warp in registers, panel solve and trailing update as in-smem DMMA products; A <- L;
-// then L^-1 by block columns (again DMMA products) -> dinv (dense 128x128, zeros above the diagonal).
-// info: atomicMin of the 1-based global index of the first non-positive pivot.  logdet += sum log d_j = log|A|.
+// One thread = one row p (32 values at P, pitch SP) of the panel below the diagonal block:  p <- p * L^-T  by forward
+// substitution against the factor at D (broadcast shared-memory reads):  x_j = (p_j - sum_{k<j} x_k L_jk) / L_jj
+__device__ __forceinline__ void row_trsm32(double* P, const double* D, const double* rdiag) {
+    double x[32];
+#pragma unroll
+    for (int j = 0; j < 32; j++) x[j] = P[j];
+#pragma unroll
+    for (int j = 0; j < 32; j++) {
+        double s0 = x[j], s1 = 0.0;
+#pragma unroll
+        for (int k = 0; k < j; k += 2) {
+            s0 = fma(-x[k], D[j * SP + k], s0);
+            if (k + 1 < j) s1 = fma(-x[k + 1], D[j * SP + k + 1], s1);
+        }
+        x[j] = (s0 + s1) * rdiag[j];
+    }
+#pragma unroll
+    for (int j = 0; j < 32; j++) P[j] = x[j];
+}
+
+// per-phase cycle counters of the leaf kernel (development aid: compile with -DBGP_LEAF_PROFILE, read with bgp_debug_leaf_clk)
+__device__ long long g_leaf_clk[8];
+#ifdef BGP_LEAF_PROFILE
+#define LEAF_CLK(i) do { if (tid == 0) { long long t_ = clock64(); g_leaf_clk[i] += t_ - t_prev; t_prev = t_; } } while (0)
+#else
+#define LEAF_CLK(i) do { (void)t_prev; } while (0)
+#endif
+
+// One CTA (8 warps): S = lower(A[0:n,0:n]) (identity-padded to 128); S <- chol(S) by 32-wide panels:
+//   warp 0 factors the diagonal 32x32 block in registers; then, concurrently, warp 0 inverts it (needed only for the
+//   final block inverse) while warps 1-3 solve the rows below by per-row substitution; the trailing update is an in-smem
+//   DMMA product by all warps.  A <- L; then L^-1 by block columns (DMMA products) -> dinv (dense 128x128, zeros above
+//   the diagonal).  info: atomicMin of the 1-based global index of the first non-positive pivot.  logdet += log|A|.
 __global__ void __launch_bounds__(256)
 leaf_potrf_trtri_kernel(double* A, int64_t lda, int n, double* dinv, int32_t* info, int64_t gofs, double* logdet) {
     extern __shared__ double sm[];
     double* S = sm;                          // [128][SP]
     double* T = S + LEAF * SP;               // [96][BP]   scratch for the inverse phase
     double* Dg = T + 96 * BP;                // [4][32][BP] inverses of the diagonal 32-blocks
+    __shared__ double rdiag[32];
+    __shared__ double colbuf[64];
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int fr = lane >> 2, fk = lane & 3;
+    long long t_prev = clock64();
 
-    for (int idx = tid; idx < LEAF * LEAF; idx += 256) {
-        const int i = idx >> 7, j = idx & (LEAF - 1);
-        double v = 0.0;
-        if (i < n) { if (j <= i) v = A[(int64_t)i * lda + j]; }
-        else if (i == j) v = 1.0;
-        S[i * SP + j] = v;
+    {
+        // 64 threads x double2 cover one 128-wide row; 4 row groups; 8 loads per thread in flight before the first store
+        const int jc = (tid & 63) * 2, rg = tid >> 6;
+        const bool vec = ((lda & 1) == 0) && ((reinterpret_cast<uintptr_t>(A) & 15) == 0);
+        for (int ib = 0; ib < LEAF; ib += 32) {
+            double2 v[8];
+#pragma unroll
+            for (int u = 0; u < 8; u++) {
+                const int i = ib + u * 4 + rg;
+                v[u] = make_double2(0.0, 0.0);
+                if (i < n && jc <= i) {
+                    const double* p = A + (int64_t)i * lda + jc;
+                    if (vec) v[u] = *reinterpret_cast<const double2*>(p);
+                    else { v[u].x = p[0]; v[u].y = p[1]; }
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < 8; u++) {
+                const int i = ib + u * 4 + rg;
+                double a0 = (jc <= i) ? v[u].x : 0.0, a1 = (jc + 1 <= i) ? v[u].y : 0.0;
+                if (i >= n) { a0 = (jc == i) ? 1.0 : 0.0; a1 = (jc + 1 == i) ? 1.0 : 0.0; }
+                S[i * SP + jc] = a0;
+                S[i * SP + jc + 1] = a1;
+            }
+        }
     }
     __syncthreads();
+    LEAF_CLK(0);
 
     double logsum = 0.0;
     for (int kb = 0; kb < 4; kb++) {
         const int c0 = kb * 32, r0 = c0 + 32, mt = (LEAF - r0) / 8;     // mt row tiles below the diagonal block
         if (warp == 0) {
             int bad;
-            logsum += warp_potrf32_inv(S + c0 * SP + c0, Dg + kb * 32 * BP, lane, &bad);
+            logsum += warp_potrf32(S + c0 * SP + c0, rdiag, colbuf, lane, &bad);
             if (bad && lane == 0) atomicMin(info, (int32_t)min((int64_t)INT_MAX, gofs + c0 + bad));
         }
         __syncthreads();
-        // panel solve  P <- P * inv(Ld)^T   (rows r0.., columns c0..c0+31); one warp owns whole row tiles (in place)
-        for (int ti = warp; ti < mt; ti += 8) {
-            double acc[4][2];
-#pragma unroll
-            for (int t = 0; t < 4; t++) acc[t][0] = acc[t][1] = 0.0;
-            const double* ap = S + (r0 + ti * 8 + fr) * SP + c0 + fk;
-            const double* bp = Dg + kb * 32 * BP + fr * BP + fk;
-#pragma unroll
-            for (int k4 = 0; k4 < 32; k4 += 4) {
-                const double av = ap[k4];
-#pragma unroll
-                for (int t = 0; t < 4; t++) dmma_leaf(acc[t][0], acc[t][1], av, bp[t * 8 * BP + k4]);
-            }
-            __syncwarp();
-            double* cp = S + (r0 + ti * 8 + fr) * SP + c0 + 2 * fk;
-#pragma unroll
-            for (int t = 0; t < 4; t++) { cp[t * 8] = acc[t][0]; cp[t * 8 + 1] = acc[t][1]; }
+        LEAF_CLK(1);
+        if (warp == 0) {
+            warp_trtri32(S + c0 * SP + c0, rdiag, Dg + kb * 32 * BP, lane);
+        } else if (warp <= 3) {
+            const int r = r0 + (warp - 1) * 32 + lane;
+            if (r < LEAF) row_trsm32(S + r * SP + c0, S + c0 * SP + c0, rdiag);
         }
         __syncthreads();
+        LEAF_CLK(2);
         // trailing update  S[i][j] -= sum_k P[i][k] P[j][k]  over lower 8x8 tiles of the remaining block
         int cnt = 0;
         for (int ti = 0; ti < mt; ti++) {
@@ -132,6 +182,7 @@ leaf_potrf_trtri_kernel(double* A, int64_t lda, int n, double* dinv, int32_t* in
             }
         }
         __syncthreads();
+        LEAF_CLK(3);
     }
     if (tid == 0 && logdet != nullptr) atomicAdd(logdet, logsum);
 
@@ -141,6 +192,7 @@ leaf_potrf_trtri_kernel(double* A, int64_t lda, int n, double* dinv, int32_t* in
         if (j <= i) A[(int64_t)i * lda + j] = S[i * SP + j];
     }
     __syncthreads();
+    LEAF_CLK(4);
     // ---- inverse: X = L^-1 in place.  Diagonal 32-blocks come from Dg; block column j (2,1,0):
     //      X[r0:, j] = -X_trail * L[r0:, j] * X_jj   with X_trail = inv(L[r0:, r0:]) already in place
     for (int idx = tid; idx < 4 * 32 * 32; idx += 256) {
@@ -186,11 +238,16 @@ leaf_potrf_trtri_kernel(double* A, int64_t lda, int n, double* dinv, int32_t* in
         }
         __syncthreads();
     }
+    LEAF_CLK(5);
     for (int idx = tid; idx < LEAF * LEAF; idx += 256) {
         const int i = idx >> 7, j = idx & (LEAF - 1);
         dinv[idx] = (j <= i) ? S[i * SP + j] : 0.0;
     }
+    __syncthreads();
+    LEAF_CLK(6);
 }
+
+void leaf_clk_read(long long* out) { cudaMemcpyFromSymbol(out, g_leaf_clk, sizeof(long long) * 8); long long z[8] = {0}; cudaMemcpyToSymbol(g_leaf_clk, z, sizeof(z)); }
 
 static int launch_leaf(Ctx* ctx, double* A, int64_t lda, int n, double* dinv, int64_t gofs, cudaStream_t st) {
     constexpr int SMEM = (LEAF * SP + 96 * BP + 4 * 32 * BP) * sizeof(double);

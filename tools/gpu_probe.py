@@ -199,3 +199,22 @@ if "ozone" in what:
     work = torch.empty(int(eng.L.bgp_gemm_nt_i8_work_bytes(n, n, k)), dtype=torch.uint8, device=dev)
     for _ in range(3): eng.gemm_nt_i8(A, A, C, alpha=-1.0, tri=True, work=work)
     torch.cuda.synchronize()
+if "leaf" in what:
+    for n in (128, 256, 512, 1024, 2048):
+        x, y = synth_field_data(n, 0)
+        xd = torch.tensor(x, device=dev); spec = E.battgp_spec()
+        K0 = eng.cov_build(spec, xd, noise=2.33e-6, symmetric=True)
+        Ks = [K0.clone() for _ in range(20)]
+        torch.cuda.synchronize()
+        info_d = torch.full((1,), 2**31 - 1, dtype=torch.int32, device=dev); ld_d = torch.zeros(1, dtype=torch.float64, device=dev)
+        eng.potrf_block(K0.clone(), info_d, ld_d); torch.cuda.synchronize()
+        e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for Kc in Ks: eng.potrf_block(Kc, info_d, ld_d)
+        e1.record(); torch.cuda.synchronize()
+        import ctypes
+        clk = (ctypes.c_longlong * 8)()
+        eng.L.bgp_debug_leaf_clk(clk)
+        nl = 21 * ((n + 127) // 128)
+        print(json.dumps({"op": "potrf_block(async)", "n": n, "us_per_call": e0.elapsed_time(e1) / 20 * 1e3,
+                          "leaf_cycles_per_phase[load,potrf32x4,subst+inv x4,trail x4,storeL,invphase,storedinv]": [int(c / nl) for c in clk][:7]}), flush=True)
