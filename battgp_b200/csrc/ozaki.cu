@@ -46,26 +46,36 @@ oz_slice_kernel(const double* __restrict__ P, int64_t rows, int64_t K, int64_t l
     __syncthreads();
     const int64_t nchunks = K / 16;
     const bool live = row < rows;
-    double m = 0.0;
+    // row maximum of |a| by integer comparison of the bit patterns: orders non-negative doubles correctly AND lets
+    // Inf / NaN win (fmax would drop a NaN), so a poisoned row is detected instead of being sliced into garbage digits
+    unsigned long long mb = 0ull;
     if (live)
         for (int64_t c = ct; c < nchunks; c += 64) {
             const double2* p = reinterpret_cast<const double2*>(P + row * ld + c * 16);
 #pragma unroll
-            for (int i = 0; i < 8; i++) { const double2 v = p[i]; m = fmax(m, fmax(fabs(v.x), fabs(v.y))); }
+            for (int i = 0; i < 8; i++) {
+                const double2 v = p[i];
+                const unsigned long long bx = (unsigned long long)__double_as_longlong(v.x) & 0x7FFFFFFFFFFFFFFFull;
+                const unsigned long long by = (unsigned long long)__double_as_longlong(v.y) & 0x7FFFFFFFFFFFFFFFull;
+                mb = max(mb, max(bx, by));
+            }
         }
-    atomicMax(&smax[r8], (unsigned long long)__double_as_longlong(m));     // non-negative doubles order like integers
+    atomicMax(&smax[r8], mb);
     __syncthreads();
-    const double rowmax = __longlong_as_double((long long)smax[r8]);
+    const unsigned long long rb_bits = smax[r8];
+    const bool poisoned = (rb_bits >> 52) == 0x7FFull;                      // Inf or NaN somewhere in the row
+    const double rowmax = __longlong_as_double((long long)rb_bits);
     int e = 0;
-    if (rowmax > 0.0) (void)frexp(rowmax, &e);                             // rowmax = f * 2^e, f in [0.5, 1)
-    if (ct == 0 && row < nrb * 128) ex[row] = scalbn(1.0, e);          // row scale 2^e
+    if (!poisoned && rowmax > 0.0) (void)frexp(rowmax, &e);                // rowmax = f * 2^e, f in [0.5, 1)
+    // row scale 2^e; NaN for a poisoned row, so that every product involving it comes out NaN like in fp64 arithmetic
+    if (ct == 0 && row < nrb * 128) ex[row] = poisoned ? __longlong_as_double(0x7FF8000000000000ll) : scalbn(1.0, e);
     const int64_t rb = row >> 7;
     const int rin = (int)(row & 127);
     for (int64_t c = ct; c < nchunks; c += 64) {
         uint32_t w[OZ_S][4];
 #pragma unroll
         for (int s = 0; s < OZ_S; s++) w[s][0] = w[s][1] = w[s][2] = w[s][3] = 0u;
-        if (live) {
+        if (live && !poisoned) {
             const double* p = P + row * ld + c * 16;
 #pragma unroll
             for (int i = 0; i < 16; i++) {

@@ -400,6 +400,8 @@ def fit(spec: KernelSpec, x: torch.Tensor, y: torch.Tensor, noise: float, *, K_o
         warnings.warn(f"A not p.d., added jitter of {jitter:.1e} to the diagonal", NumericalWarning)
     z, alpha = eng.potrs_vec(K, dinv, y)
     lml = eng.lml(z, logdet)
+    if not math.isfinite(lml):
+        raise NanError("cholesky: NaN/inf encountered in the covariance matrix or the targets")
     return FitState(spec, noise, x, K, dinv, alpha, z, logdet, lml, jitter)
 
 

@@ -77,6 +77,20 @@ def test_jitter_retry_and_not_psd(eng):
         E.fit(E.scaled_rbf_spec(3, -1.0, 1.0), _t(x), _t(y), 0.0)     # negative outputscale: never PD
 
 
+def test_nan_in_targets_or_inputs_raises(eng):
+    from battgp_b200 import engine as E
+    x, y = orc.synth_field_data(300, seed=1)
+    y2 = y.copy(); y2[17] = np.nan
+    with pytest.raises(E.NanError):
+        E.fit(E.battgp_spec(), _t(x), _t(y2), 2.33e-6)
+    x2 = x.copy(); x2[250, 2] = np.nan
+    with pytest.raises((E.NanError, E.NotPSDError)):
+        import warnings
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            E.fit(E.battgp_spec(), _t(x2), _t(y), 2.33e-6)
+
+
 def test_large_n_properties(eng):
     """N = 12288 (beyond what the CI oracle does in seconds): leading-block parity + matrix-free residual
     (SURVEY.md 8c large-N plan)."""

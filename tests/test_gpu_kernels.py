@@ -174,6 +174,30 @@ def test_gemm_nt_i8_ozaki_is_fp64_accurate(eng, M, N, K, tri):
     assert err.max().item() < 4e-16 * 8, err.max().item()
 
 
+def test_gemm_nt_i8_special_rows(eng):
+    """zero rows, denormal-sized rows, and NaN / Inf rows (poisoned rows must come out NaN as in fp64 arithmetic)."""
+    M, N, K = 256, 128, 128
+    g = torch.Generator().manual_seed(1)
+    A = torch.randn(M, K, generator=g, dtype=torch.float64)
+    B = torch.randn(N, K, generator=g, dtype=torch.float64)
+    A[3] = 0.0
+    A[7] *= 1e-290
+    B[5] *= 1e+150
+    A[11, 17] = float("nan")
+    B[9, 3] = float("inf")
+    C0 = torch.zeros(M, N, dtype=torch.float64)
+    Cd = _t(C0.numpy())
+    eng.gemm_nt_i8(_t(A.numpy()), _t(B.numpy()), Cd, alpha=1.0)
+    out = Cd.cpu()
+    ref = A @ B.T
+    assert torch.isnan(out[11]).all() and torch.isnan(out[:, 9]).all()
+    ok = torch.ones(M, N, dtype=torch.bool); ok[11] = False; ok[:, 9] = False
+    assert torch.equal(out[3][ok[3]], torch.zeros(int(ok[3].sum()), dtype=torch.float64))
+    scale = (A.abs().amax(1, keepdim=True) * B.abs().amax(1, keepdim=True).T) * K
+    err = ((out - ref).abs() / scale.clamp_min(1e-300))[ok]
+    assert torch.isfinite(out[ok]).all() and err.max().item() < 4e-15
+
+
 @pytest.mark.parametrize("n,nb", [(1300, 256), (2500, 512), (4321, 512), (5000, 1024), (6200, 2048)])
 def test_potrf_with_int8_trailing_updates_matches_lapack(eng, n, nb):
     k, _ = _spd(n, n)
