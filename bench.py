@@ -116,11 +116,7 @@ def run_reference(args, n_gpus: int):
         return
     import numpy as np
     from oracle import gp_oracle as orc
-    try:
-        from threadpoolctl import threadpool_info
-        threads = max([p.get("num_threads", 1) for p in threadpool_info()] or [1])
-    except Exception:
-        threads = os.cpu_count() or 1
+    threads = _all_host_threads()
     ns = args.ref_n
     x, y = orc.synth_field_data(ns, seed=0)
     xq = orc.query_grid(x)
@@ -148,6 +144,26 @@ def run_reference(args, n_gpus: int):
     print(json.dumps(line), flush=True)
 
 
+def _all_host_threads():
+    """torchrun exports OMP_NUM_THREADS=1 for multi-rank launches; the CPU arm must still get every host core."""
+    n = os.cpu_count() or 1
+    try:
+        from threadpoolctl import threadpool_limits
+        threadpool_limits(limits=n)
+    except Exception:
+        pass
+    try:
+        import torch
+        torch.set_num_threads(n)
+    except Exception:
+        pass
+    try:
+        from threadpoolctl import threadpool_info
+        return max([p.get("num_threads", 1) for p in threadpool_info()] or [1])
+    except Exception:
+        return n
+
+
 def workload_name(args, n_gpus):
     if args.workload == "sharded":
         return f"full_gp Wiener+RBF-ARD N={args.n} block-row-sharded Cholesky over {n_gpus} GPU(s) (BASELINE configs[4])"
@@ -160,11 +176,7 @@ def workload_name(args, n_gpus):
 def cpu_baseline(args):
     import numpy as np  # noqa: F401
     from oracle import gp_oracle as orc
-    try:
-        from threadpoolctl import threadpool_info
-        threads = max([p.get("num_threads", 1) for p in threadpool_info()] or [1])
-    except Exception:
-        threads = os.cpu_count() or 1
+    threads = _all_host_threads()
     ns = args.ref_n
     x, y = orc.synth_field_data(ns, seed=0)
     xq = orc.query_grid(x)
