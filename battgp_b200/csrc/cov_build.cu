@@ -15,6 +15,33 @@ namespace bgp {
 
 constexpr int TM = 64, TN = 128;
 
+// exp(x) for x <= 0 (RBF / Matern / Periodic arguments are never positive): range reduction by 2^k with the 2^52+2^51
+// rounding trick, degree-13 Taylor polynomial on |r| <= ln2/2 (truncation 4e-18 relative), exponent patched in by integer add.
+// ~19 FP64 instructions and no special-case branches except the flush to zero below -708.
+__device__ __forceinline__ double exp_nonpos(double x) {
+    const double t = fma(x, 1.4426950408889634074, 6755399441055744.0);
+    const int k = __double2loint(t);
+    const double kd = t - 6755399441055744.0;
+    double r = fma(kd, -6.93147180369123816490e-01, x);
+    r = fma(kd, -1.90821492927058770002e-10, r);
+    double p = 1.60590438368216145994e-10;                 // 1/13!
+    p = fma(p, r, 2.08767569878680989792e-09);
+    p = fma(p, r, 2.50521083854417187751e-08);
+    p = fma(p, r, 2.75573192239858906526e-07);
+    p = fma(p, r, 2.75573192239858906526e-06);
+    p = fma(p, r, 2.48015873015873015873e-05);
+    p = fma(p, r, 1.98412698412698412698e-04);
+    p = fma(p, r, 1.38888888888888888889e-03);
+    p = fma(p, r, 8.33333333333333333333e-03);
+    p = fma(p, r, 4.16666666666666666667e-02);
+    p = fma(p, r, 1.66666666666666666667e-01);
+    p = fma(p, r, 0.5);
+    p = fma(p, r, 1.0);
+    p = fma(p, r, 1.0);
+    const double res = __hiloint2double(__double2hiint(p) + (k << 20), __double2loint(p));
+    return x < -708.0 ? 0.0 : res;
+}
+
 // value of the kernel for one (row, col) pair given pre-scaled features; FMAX-unrolled, uniform branches
 template <int FMAX>
 __device__ __forceinline__ double eval_pair(const DevSpec& sp, const double (&rf)[FMAX], const double (&cf)[FMAX]) {
@@ -33,12 +60,12 @@ __device__ __forceinline__ double eval_pair(const DevSpec& sp, const double (&rf
                 else acc = fma(diff, diff, acc);
                 if (sp.flast[f]) {
                     double v;
-                    if (ty == BGP_RBF) v = exp(-0.5 * acc);
-                    else if (ty == BGP_PERIODIC) v = exp(-2.0 * acc);
+                    if (ty == BGP_RBF) v = exp_nonpos(-0.5 * acc);
+                    else if (ty == BGP_PERIODIC) v = exp_nonpos(-2.0 * acc);
                     else {  // Matern-5/2: r = sqrt(clamp(sqdist, 1e-30))
                         const double r = sqrt(fmax(acc, 1e-30));
                         const double s5r = 2.23606797749978969641 * r;
-                        v = (1.0 + s5r + (5.0 / 3.0) * r * r) * exp(-s5r);
+                        v = (1.0 + s5r + (5.0 / 3.0) * r * r) * exp_nonpos(-s5r);
                     }
                     ksum = fma(sp.fos[f], v, ksum);
                     acc = 0.0;
@@ -49,7 +76,18 @@ __device__ __forceinline__ double eval_pair(const DevSpec& sp, const double (&rf
     return ksum;
 }
 
-template <int FMAX>
+// BattGP's own kernel structure (cell_gp.py:32-36): feature 0 = integrated Wiener on t, features 1..3 = one RBF-ARD term.
+// Same arithmetic as eval_pair<4> with every spec-dependent branch resolved at compile time.
+__device__ __forceinline__ double eval_pair_battgp(double osw, double osr, const double (&rf)[4], const double (&cf)[4]) {
+    const double m = fmin(rf[0], cf[0]);
+    const double m2 = m * m;
+    const double w = m2 * m * (1.0 / 3.0) + fabs(rf[0] - cf[0]) * m2 * 0.5;
+    const double d1 = rf[1] - cf[1], d2 = rf[2] - cf[2], d3 = rf[3] - cf[3];
+    const double acc = fma(d3, d3, fma(d2, d2, d1 * d1));
+    return fma(osr, exp_nonpos(-0.5 * acc), osw * w);
+}
+
+template <int FMAX, bool BATTGP>
 __global__ void __launch_bounds__(256)
 cov_build_kernel(DevSpec sp, const double* __restrict__ X1, int64_t n1, int64_t ldx1,
                  const double* __restrict__ X2, int64_t n2, int64_t ldx2,
@@ -92,7 +130,8 @@ cov_build_kernel(DevSpec sp, const double* __restrict__ X1, int64_t n1, int64_t 
         double v[4];
 #pragma unroll
         for (int c = 0; c < 4; c++) {
-            v[c] = eval_pair<FMAX>(sp, rf, cf[c]);
+            if constexpr (BATTGP) v[c] = eval_pair_battgp(sp.fos[0], sp.fos[3], rf, cf[c]);
+            else v[c] = eval_pair<FMAX>(sp, rf, cf[c]);
             if (symmetric && grow == c0 + cl[c]) v[c] += sp.noise;
         }
         double* orow = out + grow * ldo + c0;
@@ -138,12 +177,16 @@ int cov_build(Ctx* ctx, const bgp_kernel_spec* spec, const double* X1, int64_t n
     if (gy > 65535) return BGP_E_ARG;
     const int vec_ok = ((ldo & 1) == 0 && ((uintptr_t)out & 15) == 0) ? 1 : 0;
     dim3 grid((unsigned)gx, (unsigned)gy);
-    if (d.nfeat <= 4)
-        cov_build_kernel<4><<<grid, 256, 0, st>>>(d, X1, n1, ldx1, X2, n2, ldx2, out, ldo, symmetric, vec_ok);
+    const bool battgp = d.nfeat == 4 && d.ftype[0] == BGP_WIENER && d.ftype[1] == BGP_RBF && d.ftype[2] == BGP_RBF &&
+                        d.ftype[3] == BGP_RBF && d.flast[0] && !d.flast[1] && !d.flast[2] && d.flast[3];
+    if (battgp)
+        cov_build_kernel<4, true><<<grid, 256, 0, st>>>(d, X1, n1, ldx1, X2, n2, ldx2, out, ldo, symmetric, vec_ok);
+    else if (d.nfeat <= 4)
+        cov_build_kernel<4, false><<<grid, 256, 0, st>>>(d, X1, n1, ldx1, X2, n2, ldx2, out, ldo, symmetric, vec_ok);
     else if (d.nfeat <= 8)
-        cov_build_kernel<8><<<grid, 256, 0, st>>>(d, X1, n1, ldx1, X2, n2, ldx2, out, ldo, symmetric, vec_ok);
+        cov_build_kernel<8, false><<<grid, 256, 0, st>>>(d, X1, n1, ldx1, X2, n2, ldx2, out, ldo, symmetric, vec_ok);
     else
-        cov_build_kernel<16><<<grid, 256, 0, st>>>(d, X1, n1, ldx1, X2, n2, ldx2, out, ldo, symmetric, vec_ok);
+        cov_build_kernel<16, false><<<grid, 256, 0, st>>>(d, X1, n1, ldx1, X2, n2, ldx2, out, ldo, symmetric, vec_ok);
     BGP_LAUNCH_OK(ctx);
     return 0;
 }
