@@ -299,7 +299,18 @@ int bgp_trsm_rlt(bgp_ctx* c, const double* L, int64_t n, int64_t ldl, const doub
     CTX_OR_FAIL(c);
     if (n == 0 || m == 0) return 0;
     if (!L || !dinv || !X || n < 0 || m < 0 || ldl < n || ldx < n || m > INT_MAX) return BGP_E_ARG;
-    return trsm_rlt_rec(ctx, L, n, ldl, dinv, X, m, ldx, (cudaStream_t)stream);
+    // stand-alone call (no factorisation in flight on this context): the int8 path of the big updates may use the whole
+    // caller-provided workspace
+    void* p0 = ctx->ws_trsm;
+    const int64_t b0 = ctx->ws_trsm_bytes;
+    if (!p0 && ctx->ws) { ctx->ws_trsm = ctx->ws; ctx->ws_trsm_bytes = ctx->ws_bytes; }
+    const int tpc = ctx->oz_tpc;
+    ctx->oz_tpc = 0;
+    const int rc = trsm_rlt_rec(ctx, L, n, ldl, dinv, X, m, ldx, (cudaStream_t)stream);
+    ctx->oz_tpc = tpc;
+    ctx->ws_trsm = p0;
+    ctx->ws_trsm_bytes = b0;
+    return rc;
 }
 
 int bgp_predict_tail(bgp_ctx* c, int64_t m, int64_t n, const double* Kq, int64_t ldk, const double* alpha,

@@ -164,6 +164,16 @@ class Engine:
             self._ws = torch.empty(need, dtype=torch.uint8, device=self.device)
             _lib.check(self.L.bgp_ctx_set_workspace(self.h, _ptr(self._ws), self._ws.numel()), "bgp_ctx_set_workspace")
 
+    def ensure_workspace_bytes(self, need: int):
+        """Make at least ``need`` bytes of int8-path scratch available (no-op when the path is off)."""
+        if not getattr(self, "ozaki", False) or need <= 0:
+            return
+        ws = getattr(self, "_ws", None)
+        if ws is None or ws.numel() < need:
+            self._ws = None
+            self._ws = torch.empty(int(need), dtype=torch.uint8, device=self.device)
+            _lib.check(self.L.bgp_ctx_set_workspace(self.h, _ptr(self._ws), self._ws.numel()), "bgp_ctx_set_workspace")
+
     def release_workspace(self):
         _lib.check(self.L.bgp_ctx_set_workspace(self.h, C.c_void_p(0), 0), "bgp_ctx_set_workspace")
         self._ws = None

@@ -61,6 +61,11 @@ class CudaOps:
         return self.eng.potrf_block(A, info, logdet)
 
     def trsm_rlt(self, L, dinv, X):
+        if self.eng.ozaki and X.shape[0] >= 1024 and L.shape[0] >= 1024:
+            # scratch for the int8 path of the big TRSM updates: digit planes of X[:, :n/2] and L21
+            k = L.shape[0] // 2
+            self.eng.ensure_workspace_bytes(int(self.eng.L.bgp_oz_slice_bytes(X.shape[0], k)) +
+                                            int(self.eng.L.bgp_oz_slice_bytes(k, k)) + 4096)
         self.eng.trsm_rlt(L, dinv, X)
 
     def gemm_nt(self, A, B, C, alpha, beta, tri=False, roff=0, coff=0):
@@ -103,6 +108,17 @@ class ShardedGP:
         self.dinv: Dict[int, torch.Tensor] = {}
         self.alpha: Optional[torch.Tensor] = None
         self.bytes_received = 0
+        self.profile = False            # True: synchronise after every phase and accumulate seconds in self.phase_s
+        self.phase_s: Dict[str, float] = {}
+
+    def _tick(self, name, t0):
+        if not self.profile:
+            return t0
+        if self.x.is_cuda:
+            torch.cuda.synchronize(self.x.device)
+        t1 = time.perf_counter()
+        self.phase_s[name] = self.phase_s.get(name, 0.0) + (t1 - t0)
+        return t1
 
     # ---- geometry
     def b0(self, i):
@@ -139,6 +155,7 @@ class ShardedGP:
     def factor(self):
         ops, P, NB = self.ops, self.P, self.NB
         info, logdet = ops.scalars()
+        t0 = time.perf_counter()
         for k in range(self.nblk):
             owner = k % P
             b0k, ek, nbk = self.b0(k), self.e(k), self.nbi(k)
@@ -153,8 +170,10 @@ class ShardedGP:
                 dkk = ops.zeros_vec(ndinv)
             if k == self.nblk - 1:
                 break
+            t0 = self._tick("diag_potrf", t0)
             self._bcast(Lkk, owner)
             self._bcast(dkk, owner)
+            t0 = self._tick("bcast", t0)
             mine = [i for i in self.owned if i > k]
             nrows = sum(self.nbi(i) for i in mine)
             # pack this rank's rows of the panel, solve them in one call, scatter back (they are part of L)
@@ -173,6 +192,7 @@ class ShardedGP:
                 for i in mine:
                     self.rows[i][:, b0k:ek].copy_(send[o:o + self.nbi(i)])
                     o += NB
+            t0 = self._tick("panel_trsm", t0)
             # exchange: every rank ends up with the whole panel, reordered into stripe order
             if P > 1:
                 assert send.is_contiguous()
@@ -188,9 +208,11 @@ class ShardedGP:
                 panel = send
             # trailing update of the owned stripes; with the int8/tcgen05 path the gathered panel is sliced ONCE and
             # every stripe's product re-uses the digit planes
+            t0 = self._tick("allgather+reorder", t0)
             use_oz = getattr(ops, "has_oz", False) and nbk % 64 == 0 and len(mine) > 0
             if use_oz:
                 self._ozbuf = ops.oz_slice(panel, getattr(self, "_ozbuf", None))
+            t0 = self._tick("slice", t0)
             for t, i in enumerate(mine):
                 b0i, ei = self.b0(i), self.e(i)
                 C = self.rows[i][:, ek:ei]
@@ -200,6 +222,7 @@ class ShardedGP:
                     A = panel[(i - k - 1) * NB:(i - k - 1) * NB + self.nbi(i)]
                     B = panel[:ei - ek]
                     ops.gemm_nt(A, B, C, -1.0, 1.0, tri=True, roff=b0i, coff=ek)
+            t0 = self._tick("trailing_update", t0)
         self._allreduce(logdet)
         self._allreduce(info, dist.ReduceOp.MIN if dist.is_initialized() else None)
         self.logdet = float(logdet.item())
@@ -260,11 +283,15 @@ class ShardedGP:
         return alpha
 
     def fit(self):
+        t0 = time.perf_counter()
         self.build()
+        t0 = self._tick("build", t0)
         info = self.factor()
         if info != 0:
             raise E.NotPSDError(f"sharded Cholesky failed at pivot {info}")
+        t0 = time.perf_counter()
         self.solve_alpha()
+        self._tick("solve_alpha", t0)
         return self
 
     def residual(self) -> float:
@@ -329,9 +356,13 @@ def bench(args, rank: int, world: int, dev: torch.device):
     spec = E.battgp_spec()
     eng = E.get_engine(dev)
 
-    def step():
-        gp = ShardedGP(spec, x, y, B.NOISE, nb=args.nb).fit()
+    def step(profile=False):
+        gp = ShardedGP(spec, x, y, B.NOISE, nb=args.nb)
+        gp.profile = profile
+        gp.fit()
+        t0 = time.perf_counter()
         mean, var = gp.predict(xq)
+        gp._tick("predict", t0)
         return gp, mean, var
 
     def sync():
@@ -362,6 +393,12 @@ def bench(args, rank: int, world: int, dev: torch.device):
     sync()
     resid = gp.residual() if args.verify else None
     del gp
+    phases = None
+    if args.phases:
+        torch.cuda.empty_cache()
+        gpp, _, _ = step(profile=True)
+        phases = {k: round(v, 4) for k, v in gpp.phase_s.items()}
+        del gpp
     ms = e0.elapsed_time(e1)
     if world > 1:
         t = torch.tensor([ms], dtype=torch.float64, device=dev)
@@ -378,7 +415,7 @@ def bench(args, rank: int, world: int, dev: torch.device):
                 "config": {"workload": B.workload_name(args, world), "n": n, "m_query": B.M_QUERY, "kernel": "wiener+rbf_ard",
                            "nb": args.nb, "fit_predict_seconds": sec, "lml": lml, "mean0": float(mean[0]), "var0": float(var[0]),
                            "nccl_bytes_received_per_rank_per_step": recv,
-                           "residual_Kalpha_minus_y_over_y": resid,
+                           "residual_Kalpha_minus_y_over_y": resid, "phase_seconds_rank0_synchronised": phases,
                            "l2_policy": "inputs_exceed_l2 (per-rank stripes rebuilt every step)"},
                 "clocks": clocks, "gpu_launches": int(launches),
                 "e2e": {"value": flops / sec * 1e-9, "unit": "GF/s", "note": "X,y replicated in HBM; host e2e measured on the per_gpu workload",

@@ -340,6 +340,7 @@ def main():
     ap.add_argument("--ref-n", type=int, default=10000, help="sample size of the CPU arm / cpu_baseline")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--verify", action="store_true", help="sharded workload: also report the matrix-free residual |K alpha - y|/|y|")
+    ap.add_argument("--phases", action="store_true", help="sharded workload: extra synchronised pass reporting seconds per phase")
     ap.add_argument("--nb", type=int, default=1024, help="stripe height of the sharded workload")
     args = ap.parse_args()
     if args.impl == "reference":

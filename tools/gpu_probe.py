@@ -218,3 +218,20 @@ if "leaf" in what:
         nl = 21 * ((n + 127) // 128)
         print(json.dumps({"op": "potrf_block(async)", "n": n, "us_per_call": e0.elapsed_time(e1) / 20 * 1e3,
                           "leaf_cycles_per_phase[load,potrf32x4,subst+inv x4,trail x4,storeL,invphase,storedinv]": [int(c / nl) for c in clk][:7]}), flush=True)
+
+if "nbsweep" in what:
+    n = 40000
+    x, y = synth_field_data(n, 0)
+    xd = torch.tensor(x, device=dev); spec = E.battgp_spec()
+    K = E.alloc_matrix(n, n, dev)
+    for nb, tpc, la in ((1024, 2, 1), (1536, 2, 1), (2048, 2, 1), (2560, 2, 1), (3072, 2, 1), (2048, 1, 1), (2048, 3, 1), (1536, 1, 1), (2048, 0, 0), (1024, 0, 0)):
+        eng.set("nb", nb); eng.set("ozaki", 1); eng.set("oz_tpc", tpc); eng.set("lookahead", la)
+        best = 1e30
+        for r in range(2):
+            eng.cov_build(spec, xd, noise=2.33e-6, symmetric=True, out=K)
+            torch.cuda.synchronize()
+            e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+            e0.record(); info, ld, dinv = eng.potrf(K); e1.record(); torch.cuda.synchronize()
+            best = min(best, e0.elapsed_time(e1))
+        print(json.dumps({"op": "potrf_sweep", "n": n, "nb": nb, "tpc": tpc, "lookahead": la, "info": info, "ms": best}), flush=True)
+    eng.set("nb", 0); eng.set("oz_tpc", 2); eng.set("lookahead", 1)
