@@ -17,7 +17,8 @@ constexpr int TM = 64, TN = 128;
 
 // exp(x) for x <= 0 (RBF / Matern / Periodic arguments are never positive): range reduction by 2^k with the 2^52+2^51
 // rounding trick, degree-13 Taylor polynomial on |r| <= ln2/2 (truncation 4e-18 relative), exponent patched in by integer add.
-// ~19 FP64 instructions and no special-case branches except the flush to zero below -708.
+// ~19 FP64 instructions; the only special case is x < -708 (result near / below the smallest normal), which takes
+// libdevice's exp().
 __device__ __forceinline__ double exp_nonpos(double x) {
     const double t = fma(x, 1.4426950408889634074, 6755399441055744.0);
     const int k = __double2loint(t);
@@ -39,7 +40,8 @@ __device__ __forceinline__ double exp_nonpos(double x) {
     p = fma(p, r, 1.0);
     p = fma(p, r, 1.0);
     const double res = __hiloint2double(__double2hiint(p) + (k << 20), __double2loint(p));
-    return x < -708.0 ? 0.0 : res;
+    if (x < -708.0) return exp(x);        // (sub)normal boundary: rare, take libdevice's careful path
+    return res;
 }
 
 // value of the kernel for one (row, col) pair given pre-scaled features; FMAX-unrolled, uniform branches
