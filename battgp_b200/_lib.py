@@ -58,6 +58,7 @@ SIGNATURES = {
     "bgp_gemm_nt_i8": (C.c_int, [_P, _I64, _I64, _I64, _D, _P, _I64, _P, _I64, _P, _I64, C.c_int, _I64, _I64, _P, _I64, _P]),
     "bgp_potrf_dinv_elems": (_I64, [_I64]),
     "bgp_potrf": (C.c_int, [_P, _P, _I64, _I64, _P, C.POINTER(_D), _P]),
+    "bgp_potrf_aug": (C.c_int, [_P, _P, _I64, _I64, _I64, _P, C.POINTER(_D), _P]),
     "bgp_potrf_block": (C.c_int, [_P, _P, _I64, _I64, _P, _P, _P, _P]),
     "bgp_potrs_vec": (C.c_int, [_P, _P, _I64, _I64, _P, _P, _P, _P, _P]),
     "bgp_trsm_rlt": (C.c_int, [_P, _P, _I64, _I64, _P, _P, _I64, _I64, _P]),

@@ -57,13 +57,22 @@ static inline int64_t effective_nb(const Ctx* ctx, int64_t n) {
 }
 
 // Right-looking over NB-wide panels with one panel of look-ahead (see potrf.cu header comment).
-static int potrf_driver(Ctx* ctx, double* A, int64_t n, int64_t lda, double* dinv, cudaStream_t mainst) {
-    const int64_t NB = effective_nb(ctx, n);
-    if (!ctx->lookahead || n <= 2 * NB) return potrf_rec(ctx, A, n, lda, dinv, 0, mainst);
+// A is (n + mx) x n: the first n rows are the symmetric matrix (lower triangle), the mx EXTRA rows ride along -- they take
+// part in every panel solve and trailing update, so they come out as X L^-T (predictive-variance solve fused into the
+// factorisation: the M = 300 query rows are processed by the big tiles of the trailing updates instead of a separate
+// recursive TRSM).
+static int potrf_driver(Ctx* ctx, double* A, int64_t n, int64_t mx, int64_t lda, double* dinv, cudaStream_t mainst) {
+    const int64_t R = n + mx;
+    const int64_t NB = effective_nb(ctx, R);
+    if (!ctx->lookahead || n <= 2 * NB) {
+        int rc = potrf_rec(ctx, A, n, lda, dinv, 0, mainst);
+        if (!rc && mx > 0) rc = trsm_rlt_rec(ctx, A, n, lda, dinv, A + n * lda, mx, lda, mainst);
+        return rc;
+    }
     cudaStream_t P = ctx->panel_stream;
     // int8/tcgen05 trailing updates (ozaki.cu): two slice buffers (panel k is still being read by T_k on the caller's
     // stream while panel k+1 is sliced on the panel stream)
-    const int64_t ozbytes = ((oz_slice_buffer_bytes(n - NB, NB) + 255) / 256) * 256;
+    const int64_t ozbytes = ((oz_slice_buffer_bytes(R - NB, NB) + 255) / 256) * 256;
     const bool oz = ctx->ozaki && ctx->ws && (NB % 64 == 0) && ((lda & 1) == 0) && (((uintptr_t)A & 15) == 0) &&
                     (((uintptr_t)ctx->ws & 255) == 0) && ctx->ws_bytes >= 2 * ozbytes;
     void* ozbuf[2] = {ctx->ws, reinterpret_cast<char*>(ctx->ws) + ozbytes};
@@ -80,7 +89,7 @@ static int potrf_driver(Ctx* ctx, double* A, int64_t n, int64_t lda, double* din
     for (int64_t k = 0; k < npanels; k++) {
         const int64_t k0 = k * NB;
         const int64_t nbk = (n - k0 < NB) ? n - k0 : NB;
-        const int64_t below = n - k0 - nbk;
+        const int64_t below = R - k0 - nbk;                    // rows under the diagonal block, extra rows included
         double* Akk = A + k0 * lda + k0;
         double* dinv_k = dinv + (k0 / LEAF) * (int64_t)LEAF * LEAF;
         int rc;
@@ -89,28 +98,28 @@ static int potrf_driver(Ctx* ctx, double* A, int64_t n, int64_t lda, double* din
             if (k >= 2) BGP_CUDA_OK(cudaStreamWaitEvent(P, ctx->ev_trail[(k - 2) % 3], 0));
             if (oz) {
                 // panel k-1 was sliced (rows k0.. of it are rows 0.. of its slice buffer)
-                if ((rc = oz_gemm(ctx, ozbuf[(k - 1) & 1], n - k0, 0, ozbuf[(k - 1) & 1], n - k0, 0, n - k0, nbk, NB, -1.0, Akk, lda,
+                if ((rc = oz_gemm(ctx, ozbuf[(k - 1) & 1], R - k0, 0, ozbuf[(k - 1) & 1], R - k0, 0, R - k0, nbk, NB, -1.0, Akk, lda,
                                   1, 0, 0, P, ctx->oz_tpc))) return rc;
             } else {
                 const double* Lp = A + k0 * lda + (k0 - NB);     // rows k0.., columns of panel k-1
-                GemmArgs g{Lp, lda, Lp, lda, Akk, lda, (int)(n - k0), (int)nbk, (int)NB, -1.0, 1.0, 1, 0, 0};
+                GemmArgs g{Lp, lda, Lp, lda, Akk, lda, (int)(R - k0), (int)nbk, (int)NB, -1.0, 1.0, 1, 0, 0};
                 if ((rc = gemm_nt(ctx, g, P))) return rc;
             }
         }
         if ((rc = potrf_rec(ctx, Akk, nbk, lda, dinv_k, k0, P))) return rc;
         if (below > 0 && (rc = trsm_rlt_rec(ctx, Akk, nbk, lda, dinv_k, Akk + nbk * lda, below, lda, P))) return rc;
-        if (oz && below > 0 && (rc = oz_slice(ctx, Akk + nbk * lda, below, nbk, lda, ozbuf[k & 1], P))) return rc;
+        const int64_t t0 = k0 + nbk + NB;
+        if (oz && t0 - NB < n && below > 0 && nbk == NB && (rc = oz_slice(ctx, Akk + nbk * lda, below, nbk, lda, ozbuf[k & 1], P))) return rc;
         BGP_CUDA_OK(cudaEventRecord(ctx->ev_panel[k % 2], P));
         // ---- T_k (caller's stream): rank-nbk update of everything right of column block k+1
-        const int64_t t0 = k0 + nbk + NB;
         if (t0 < n) {
             BGP_CUDA_OK(cudaStreamWaitEvent(mainst, ctx->ev_panel[k % 2], 0));
             if (oz) {
-                if ((rc = oz_gemm(ctx, ozbuf[k & 1], below, NB, ozbuf[k & 1], below, NB, n - t0, n - t0, nbk, -1.0,
+                if ((rc = oz_gemm(ctx, ozbuf[k & 1], below, NB, ozbuf[k & 1], below, NB, R - t0, n - t0, nbk, -1.0,
                                   A + t0 * lda + t0, lda, 1, 0, 0, mainst, ctx->oz_tpc))) return rc;
             } else {
                 const double* Lt = A + t0 * lda + k0;
-                GemmArgs g{Lt, lda, Lt, lda, A + t0 * lda + t0, lda, (int)(n - t0), (int)(n - t0), (int)nbk, -1.0, 1.0, 1, 0, 0};
+                GemmArgs g{Lt, lda, Lt, lda, A + t0 * lda + t0, lda, (int)(R - t0), (int)(n - t0), (int)nbk, -1.0, 1.0, 1, 0, 0};
                 if ((rc = gemm_nt(ctx, g, mainst))) return rc;
             }
             BGP_CUDA_OK(cudaEventRecord(ctx->ev_trail[k % 3], mainst));
@@ -248,14 +257,18 @@ int bgp_gemm_nt(bgp_ctx* c, int64_t M, int64_t N, int64_t K, double alpha, const
 int64_t bgp_potrf_dinv_elems(int64_t n) { return n <= 0 ? 0 : ((n + LEAF - 1) / LEAF) * (int64_t)LEAF * LEAF; }
 
 int bgp_potrf(bgp_ctx* c, double* A, int64_t n, int64_t lda, double* dinv, double* logdet_host, void* stream) {
+    return bgp_potrf_aug(c, A, n, 0, lda, dinv, logdet_host, stream);
+}
+
+int bgp_potrf_aug(bgp_ctx* c, double* A, int64_t n, int64_t mx, int64_t lda, double* dinv, double* logdet_host, void* stream) {
     CTX_OR_FAIL(c);
-    if (n < 0 || n > INT_MAX) return BGP_E_ARG;
+    if (n < 0 || mx < 0 || n + mx > INT_MAX) return BGP_E_ARG;
     if (n == 0) { if (logdet_host) *logdet_host = 0.0; return 0; }
     if (!A || !dinv || lda < n) return BGP_E_ARG;
     cudaStream_t st = (cudaStream_t)stream;
     init_scalars_kernel<<<1, 32, 0, st>>>(ctx->d_info, ctx->d_scal);
     BGP_LAUNCH_OK(ctx);
-    int rc = potrf_driver(ctx, A, n, lda, dinv, st);
+    int rc = potrf_driver(ctx, A, n, mx, lda, dinv, st);
     if (rc) return rc;
     int32_t info = 0;
     double ld = 0.0;

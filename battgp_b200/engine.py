@@ -257,14 +257,18 @@ class Engine:
 
     # ------------------------------------------------------------------ K4
     def potrf(self, A: torch.Tensor):
-        """In-place lower Cholesky.  Returns (info, logdet, dinv)."""
+        """In-place lower Cholesky.  ``A`` is n x n, or (n + mx) x n with mx extra right-hand-side rows that leave as
+        X L^-T (bgp_potrf_aug).  Returns (info, logdet, dinv)."""
         _check_f64_cuda(A, "A", self.device)
-        n = A.shape[0]
+        n = A.shape[1]
+        mx = A.shape[0] - n
+        if mx < 0:
+            raise ValueError("potrf: expected n x n or (n + mx) x n")
         dinv = torch.empty(int(self.L.bgp_potrf_dinv_elems(n)), dtype=torch.float64, device=self.device)
-        self._ensure_workspace(n)
+        self._ensure_workspace(n + mx)
         logdet = C.c_double(0.0)
-        rc = self.L.bgp_potrf(self.h, _ptr(A), n, self._ld(A), _ptr(dinv), C.byref(logdet), self._stream())
-        _lib.check(rc, "bgp_potrf")
+        rc = self.L.bgp_potrf_aug(self.h, _ptr(A), n, mx, self._ld(A), _ptr(dinv), C.byref(logdet), self._stream())
+        _lib.check(rc, "bgp_potrf_aug")
         return rc, logdet.value, dinv
 
     # ------------------------------------------------------------------ K5
@@ -379,24 +383,39 @@ class FitState:
     logdet: float
     lml: float
     jitter: float = 0.0
+    xq: Optional[torch.Tensor] = None       # query points whose solve V = K_*N L^-T came out of the factorisation
+    V: Optional[torch.Tensor] = None
 
 
 def fit(spec: KernelSpec, x: torch.Tensor, y: torch.Tensor, noise: float, *, K_out: Optional[torch.Tensor] = None,
-        kbuilder=None, potrf_events=None) -> FitState:
+        kbuilder=None, potrf_events=None, xq: Optional[torch.Tensor] = None, kcross=None) -> FitState:
     """build K -> Cholesky (with GPyTorch's jitter retries) -> alpha -> LML.  ``kbuilder(out, extra_noise)`` may
-    replace the fused build for kernels the engine does not know (it must fill the lower triangle of ``out``)."""
+    replace the fused build for kernels the engine does not know (it must fill the lower triangle of ``out``).
+
+    With ``xq`` (M query points) the cross-covariance rows K_*N are appended under K and ride through the factorisation
+    (bgp_potrf_aug): the state then already holds V = K_*N L^-T for the predictive variance -- BattGP builds a model,
+    predicts once at 300 points and frees it (battgp_full.py:98-120), so fit and predict are one pass here."""
     eng = get_engine(x.device)
     n = x.shape[0]
-    K = K_out if K_out is not None else alloc_matrix(n, n, x.device)
+    m = 0 if xq is None else xq.shape[0]
+    Kfull = K_out if K_out is not None else alloc_matrix(n + m, n, x.device)
+    if Kfull.shape[0] != n + m:
+        raise ValueError(f"K_out must have {n + m} rows")
+    K = Kfull[:n]
     jitter = 0.0
     for attempt in range(len(JITTERS_F64) + 1):
         if kbuilder is None:
             eng.cov_build(spec, x, noise=noise + jitter, symmetric=True, out=K)
         else:
             kbuilder(K, noise + jitter)
+        if m:
+            if kcross is None:
+                eng.cov_build(spec, xq, x, out=Kfull[n:])
+            else:
+                Kfull[n:].copy_(kcross)
         if potrf_events is not None:
             potrf_events[0].record()
-        info, logdet, dinv = eng.potrf(K)
+        info, logdet, dinv = eng.potrf(Kfull)
         if potrf_events is not None:
             potrf_events[1].record()
         if info == 0 and math.isfinite(logdet):
@@ -412,7 +431,10 @@ def fit(spec: KernelSpec, x: torch.Tensor, y: torch.Tensor, noise: float, *, K_o
     lml = eng.lml(z, logdet)
     if not math.isfinite(lml):
         raise NanError("cholesky: NaN/inf encountered in the covariance matrix or the targets")
-    return FitState(spec, noise, x, K, dinv, alpha, z, logdet, lml, jitter)
+    st = FitState(spec, noise, x, K, dinv, alpha, z, logdet, lml, jitter)
+    if m:
+        st.xq, st.V = xq, Kfull[n:]
+    return st
 
 
 def predict(st: FitState, xq: torch.Tensor, *, full_cov: bool = False, clamp: bool = True, kcross=None, kdiag=None):
@@ -420,7 +442,10 @@ def predict(st: FitState, xq: torch.Tensor, *, full_cov: bool = False, clamp: bo
     eng = get_engine(st.x.device)
     Kq = eng.cov_build(st.spec, xq, st.x) if kcross is None else kcross
     mean, _ = eng.predict_tail(Kq=Kq, alpha=st.alpha)
-    V = eng.trsm_rlt(st.L, st.dinv, Kq)          # in place: Kq now holds K_*N L^-T
+    if st.V is not None and st.xq is not None and (st.xq is xq or (st.xq.shape == xq.shape and torch.equal(st.xq, xq))):
+        V = st.V                                 # solved during the factorisation (fit(..., xq=...))
+    else:
+        V = eng.trsm_rlt(st.L, st.dinv, Kq)      # in place: Kq now holds K_*N L^-T
     if full_cov:
         m = xq.shape[0]
         Cq = eng.cov_build(st.spec, xq, xq) if kdiag is None else kdiag

@@ -32,10 +32,11 @@ class PosteriorCovariance:
     """Lazy posterior covariance of the latent f at the query points: k** - V V^T, V = K_*N L^-T (no noise added --
     recursive_gp.py:120 "add no noise_var to be consistent with gpytorch")."""
 
-    def __init__(self, model, state: E.FitState, kernel: Kernel, xq: torch.Tensor, Kq: torch.Tensor, out_dtype, out_device):
+    def __init__(self, model, state: E.FitState, kernel: Kernel, xq: torch.Tensor, Kq: torch.Tensor, out_dtype, out_device,
+                 V: Optional[torch.Tensor] = None):
         self.model, self.state, self.kernel, self.xq, self.Kq = model, state, kernel, xq, Kq
         self.out_dtype, self.out_device = out_dtype, out_device
-        self._V: Optional[torch.Tensor] = None
+        self._V: Optional[torch.Tensor] = V      # already solved when the query rows rode through the factorisation
 
     @property
     def shape(self):
@@ -77,6 +78,11 @@ class PosteriorCovariance:
 
     def numpy(self):
         return self.to_dense().cpu().numpy()
+
+    def add_diagonal(self, noise):
+        """likelihood(model(x)): predictive covariance of y = f + eps (dense; small M x M)."""
+        c = self.to_dense()
+        return c + torch.diag_embed(noise.to(c).expand(c.shape[-1]))
 
 
 class ExactGP(GP):
@@ -123,7 +129,9 @@ class ExactGP(GP):
         ps = [p.detach().reshape(-1).to(torch.float64) for p in self.parameters()]
         return tuple(torch.cat(ps).tolist()) if ps else ()
 
-    def _fit_state(self):
+    def _fit_state(self, xq=None):
+        """(Re)factorise when no valid cache exists.  ``xq``: query points of the call that triggers the fit -- their
+        cross-covariance rows are appended to K and solved inside the factorisation (E.fit(..., xq=...))."""
         sig = self._signature()
         if self.prediction_strategy is not None and self.prediction_strategy[0] == sig:
             return self.prediction_strategy[1], self.prediction_strategy[2]
@@ -139,7 +147,7 @@ class ExactGP(GP):
         noise = float(self.likelihood.noise.detach().reshape(-1)[0])
         binding = bind_spec(kernel, train_x.shape[-1])
         if binding is not None:
-            st = E.fit(binding.to_spec(), x64, resid, noise)
+            st = E.fit(binding.to_spec(), x64, resid, noise, xq=None if xq is None else _stage(xq, dev))
         else:
             def kbuilder(out, nz):
                 k = dense_cov(kernel, train_x, train_x).to(device=dev, dtype=torch.float64)
@@ -164,7 +172,7 @@ class ExactGP(GP):
         if settings.debug.on() and all(a.shape == b.shape and torch.equal(a, b) for a, b in zip(self.train_inputs, inputs)):
             warnings.warn("The input matches the stored training data. Did you forget to call model.train()?", GPInputWarning)
         xq = inputs[0]
-        st, kernel = self._fit_state()
+        st, kernel = self._fit_state(xq)
         test_prior = self.forward(*inputs, **kwargs)
         dev = st.x.device
         eng = E.get_engine(dev)
@@ -177,4 +185,7 @@ class ExactGP(GP):
             Kq.copy_(dense_cov(kernel, xq, self.train_inputs[0]).to(device=dev, dtype=torch.float64))
         mean, _ = eng.predict_tail(Kq=Kq, alpha=st.alpha)
         mean = mean.to(device=xq.device, dtype=xq.dtype) + test_prior.mean
-        return MultivariateNormal(mean, PosteriorCovariance(self, st, kernel, xq, Kq, xq.dtype, xq.device))
+        V = None
+        if st.V is not None and st.xq is not None and st.xq.shape == xq64.shape and torch.equal(st.xq, xq64):
+            V = st.V                                 # this call triggered the fit: the solve is already done
+        return MultivariateNormal(mean, PosteriorCovariance(self, st, kernel, xq, Kq, xq.dtype, xq.device, V=V))

@@ -129,6 +129,10 @@ int bgp_oz_gemm(bgp_ctx* ctx, const void* bufA, int64_t rowsA, int64_t arow0, co
  * Synchronises `stream` at the end (it has to return info).  logdet (host, may be NULL) = 2*sum(log L_ii). */
 int64_t bgp_potrf_dinv_elems(int64_t n);
 int bgp_potrf(bgp_ctx* ctx, double* A, int64_t n, int64_t lda, double* dinv, double* logdet_host, void* stream);
+/* Same, for an augmented (n + mx) x n matrix: rows n.. hold mx extra right-hand-side ROWS X (e.g. K_*N of the M = 300
+ * query points, battgp_full.py:98) which leave as X L^-T -- the predictive-variance solve of bgp_trsm_rlt fused into the
+ * panel solves / trailing updates of the factorisation.  Workspace: bgp_potrf_workspace_bytes(ctx, n + mx). */
+int bgp_potrf_aug(bgp_ctx* ctx, double* A, int64_t n, int64_t mx, int64_t lda, double* dinv, double* logdet_host, void* stream);
 
 /* ---- K5: alpha = K^-1 y via two triangular sweeps (HBM-bound) -------------------------------------------
  * replaces cholesky_solve for the mean cache of DefaultPredictionStrategy / inv_quad of the mll.

@@ -36,6 +36,35 @@ def test_config1_battgp_fit_predict_matches_oracle(eng, n):
     assert st.jitter == 0.0
 
 
+@pytest.mark.parametrize("n,nb", [(700, 0), (3000, 512), (5000, 1024), (4321, 1024)])
+def test_fused_fit_predict_matches_oracle(eng, n, nb):
+    """fit(..., xq=...) appends K_*N to the matrix being factorised (bgp_potrf_aug); mean/var must equal the two-step path
+    and the oracle."""
+    from battgp_b200 import engine as E
+    x, y = orc.synth_field_data(n, seed=21)
+    xq = orc.query_grid(x)
+    f = orc.fit(orc.battgp_spec(), x, y, 2.33e-6)
+    mr, vr = orc.predict(orc.battgp_spec(), x, f, xq)
+    eng.set("nb", nb)
+    try:
+        st = E.fit(E.battgp_spec(), _t(x), _t(y), 2.33e-6, xq=_t(xq))
+        assert st.V is not None and st.V.shape == (300, n)
+        m, v = E.predict(st, _t(xq))
+        st2 = E.fit(E.battgp_spec(), _t(x), _t(y), 2.33e-6)
+        m2, v2 = E.predict(st2, _t(xq))
+    finally:
+        eng.set("nb", 0)
+    np.testing.assert_allclose(m.cpu().numpy(), mr, rtol=1e-7)
+    np.testing.assert_allclose(v.cpu().numpy(), vr, rtol=1e-6)
+    np.testing.assert_allclose(v.cpu().numpy(), v2.cpu().numpy(), rtol=1e-7)
+    assert abs(st.lml - f.lml) < 1e-9 * abs(f.lml)
+    # a different query set falls back to the stand-alone solve
+    xq3 = xq[:7] + 0.25
+    m3, v3 = E.predict(st, _t(xq3))
+    m3r, v3r = orc.predict(orc.battgp_spec(), x, f, xq3)
+    np.testing.assert_allclose(v3.cpu().numpy(), v3r, rtol=1e-6)
+
+
 def test_scaled_rbf_full_cov_matches_oracle(eng):
     from battgp_b200 import engine as E
     rng = np.random.default_rng(7)
