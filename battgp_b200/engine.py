@@ -454,3 +454,23 @@ def predict(st: FitState, xq: torch.Tensor, *, full_cov: bool = False, clamp: bo
     kd = eng.cov_diag(st.spec, xq) if kdiag is None else kdiag
     _, var = eng.predict_tail(V=V, kdiag=kd, min_var=MIN_VARIANCE_F64 if clamp else -math.inf)
     return mean, var
+
+
+def residual(st: FitState, y: torch.Tensor, block: int = 2048) -> float:
+    """Matrix-free check at any size: ||K alpha - y|| / ||y|| with K REBUILT from X row-block by row-block (full width),
+    so it does not depend on the factor that produced alpha."""
+    eng = get_engine(st.x.device)
+    n = st.x.shape[0]
+    a_row = alloc_matrix(1, n, st.x.device)
+    a_row[0].copy_(st.alpha)
+    rr = torch.zeros(1, dtype=torch.float64, device=st.x.device)
+    for b0 in range(0, n, block):
+        e = min(n, b0 + block)
+        krow = eng.cov_build(st.spec, st.x[b0:e], st.x)
+        r = alloc_matrix(e - b0, 1, st.x.device)
+        r[:, 0].copy_((st.noise + st.jitter) * st.alpha[b0:e] - y[b0:e])
+        eng.gemm_nt(krow, a_row, r, alpha=1.0, beta=1.0)
+        rt = alloc_matrix(1, e - b0, st.x.device)
+        rt[0].copy_(r[:, 0])
+        eng.rowsumsq(rt, rr, True)
+    return math.sqrt(float(rr.item())) / float(torch.linalg.vector_norm(y).item())

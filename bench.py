@@ -31,8 +31,8 @@ M_QUERY = 300
 NOISE = 2.33e-6
 FP64_DMMA_PEAK_TFLOPS = 37.1   # measured on this pool's B200: profiles/fp64_peak_r01.txt (MEASURED_PEAKS.json has no fp64 entry)
 # dram__bytes_read.sum + dram__bytes_write.sum summed over the kernels of one bgp_potrf call, from the committed ncu launch
-# lists (profiles/launches_r01_ozaki_summary.txt: int8 path 275 GB; launches_r01_summary.txt: DMMA-only path 315 GB) -- N -> bytes
-TRAFFIC_BYTES_PER_POTRF = {40000: 2.75e11}
+# lists (profiles/launches_r01_final_summary.txt: int8 path 280 GB; launches_r01_summary.txt: DMMA-only path 315 GB) -- N -> bytes
+TRAFFIC_BYTES_PER_POTRF = {40000: 2.8e11}
 
 
 def algorithmic_flops(n: int, m: int = M_QUERY) -> float:
@@ -272,6 +272,12 @@ def run_gpu(args, n_gpus: int):
     step_e2e()
     ms_e2e = timed(step_e2e, args.steps)
 
+    # outside the timed region: parity evidence at the full size -- matrix-free residual and the oracle-free identity
+    st_chk, mean_chk, var_chk = step_device()
+    resid = E.residual(st_chk, yd)
+    finite = bool(torch.isfinite(mean_chk).all() and torch.isfinite(var_chk).all() and (var_chk > 0).all())
+    lml_chk = st_chk.lml
+    del st_chk
     flops = algorithmic_flops(n)
     sec = ms_total / 1e3 / args.steps
     sec_e2e = ms_e2e / 1e3 / args.steps
@@ -315,7 +321,8 @@ def run_gpu(args, n_gpus: int):
         "dtype": "f64", "data": "synthetic",
         "config": {"workload": workload_name(args, world), "n": n, "m_query": M_QUERY, "kernel": "wiener+rbf_ard",
                    "l2_policy": "inputs_exceed_l2 (K is %.1f GB per GPU, rebuilt every step)" % (8.0 * n * n / 1e9),
-                   "fit_predict_seconds": sec, "potrf_ms": pm, "trailing_update_path": "int8_tcgen05_ozaki" if eng.ozaki else "fp64_dmma"},
+                   "fit_predict_seconds": sec, "potrf_ms": pm, "trailing_update_path": "int8_tcgen05_ozaki" if eng.ozaki else "fp64_dmma",
+                   "residual_Kalpha_minus_y_over_y": resid, "lml": lml_chk, "predictions_finite_and_positive": finite},
         "clocks": clocks,
         "e2e": {"value": e2e_value, "unit": "GF/s", "seconds": sec_e2e,
                 "h2d_bytes_per_step": int(xh.numel() + yh.numel() + xqh.numel()) * 8, "d2h_bytes_per_step": 2 * M_QUERY * 8},

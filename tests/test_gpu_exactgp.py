@@ -136,6 +136,7 @@ def test_large_n_properties(eng):
     K = eng.cov_build(E.battgp_spec(), xd, xd)
     r = K @ st.alpha + 2.33e-6 * st.alpha - yd
     assert (r.norm() / yd.norm()).item() < 1e-8
+    assert E.residual(st, yd) < 1e-8
     # (iii) variance is within [min_var, prior variance]
     xq = _t(orc.query_grid(x))
     m, v = E.predict(st, xq)
