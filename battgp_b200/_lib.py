@@ -53,6 +53,7 @@ SIGNATURES = {
     "bgp_gemm_nt": (C.c_int, [_P, _I64, _I64, _I64, _D, _P, _I64, _P, _I64, _D, _P, _I64, C.c_int, _I64, _I64, _P]),
     "bgp_oz_slice_bytes": (_I64, [_I64, _I64]),
     "bgp_oz_slice": (C.c_int, [_P, _P, _I64, _I64, _I64, _P, _I64, _P]),
+    "bgp_oz_slice_gather": (C.c_int, [_P, _P, _I64, _I64, _I64, _P, _I64, _P, _I64, _P]),
     "bgp_oz_gemm": (C.c_int, [_P, _P, _I64, _I64, _P, _I64, _I64, _I64, _I64, _I64, _D, _P, _I64, C.c_int, _I64, _I64, _P]),
     "bgp_gemm_nt_i8_work_bytes": (_I64, [_I64, _I64, _I64]),
     "bgp_gemm_nt_i8": (C.c_int, [_P, _I64, _I64, _I64, _D, _P, _I64, _P, _I64, _P, _I64, C.c_int, _I64, _I64, _P, _I64, _P]),

@@ -23,7 +23,7 @@ int predict_tail(Ctx*, int64_t, int64_t, const double*, int64_t, const double*, 
 int gemv_t(Ctx*, const double*, int64_t, int64_t, int64_t, const double*, double*, double, cudaStream_t);
 int rowsumsq(Ctx*, const double*, int64_t, int64_t, int64_t, double*, int, cudaStream_t);
 int64_t oz_slice_buffer_bytes(int64_t rows, int64_t K);
-int oz_slice(Ctx*, const double*, int64_t, int64_t, int64_t, void*, cudaStream_t);
+int oz_slice(Ctx*, const double*, int64_t, int64_t, int64_t, void*, cudaStream_t, const int32_t* blkmap = nullptr, int64_t blkrows = 0);
 int oz_gemm(Ctx*, const void*, int64_t, int64_t, const void*, int64_t, int64_t, int64_t, int64_t, int64_t, double, double*,
             int64_t, int, int64_t, int64_t, cudaStream_t, int tiles_per_cta = 0);
 int potri(Ctx*, double*, int64_t, int64_t, const double*, double*, int64_t, cudaStream_t);
@@ -379,6 +379,15 @@ int bgp_oz_slice(bgp_ctx* c, const double* P, int64_t rows, int64_t K, int64_t l
     if (rows <= 0) return 0;
     if (!P || !buf || K <= 0 || K % 64 || ld < K || buf_bytes < oz_slice_buffer_bytes(rows, K) || ((uintptr_t)buf & 255)) return BGP_E_ARG;
     return oz_slice(ctx, P, rows, K, ld, buf, (cudaStream_t)stream);
+}
+
+int bgp_oz_slice_gather(bgp_ctx* c, const double* P, int64_t rows, int64_t K, int64_t ld, const int32_t* blkmap, int64_t blkrows,
+                        void* buf, int64_t buf_bytes, void* stream) {
+    CTX_OR_FAIL(c);
+    if (rows <= 0) return 0;
+    if (!P || !buf || !blkmap || blkrows <= 0 || K <= 0 || K % 64 || ld < K || buf_bytes < oz_slice_buffer_bytes(rows, K) ||
+        ((uintptr_t)buf & 255)) return BGP_E_ARG;
+    return oz_slice(ctx, P, rows, K, ld, buf, (cudaStream_t)stream, blkmap, blkrows);
 }
 
 int bgp_oz_gemm(bgp_ctx* c, const void* bufA, int64_t rowsA, int64_t arow0, const void* bufB, int64_t rowsB, int64_t brow0,

@@ -38,10 +38,13 @@ __device__ __forceinline__ int oz_swz64(int r8, int kb64) {
 // grid.x = ceil(rows_pad / 8); block = 512 threads = 8 rows x 64 chunk-threads
 __global__ void __launch_bounds__(512)
 oz_slice_kernel(const double* __restrict__ P, int64_t rows, int64_t K, int64_t ld, int8_t* __restrict__ out,
-                double* __restrict__ ex, int64_t nrb) {
+                double* __restrict__ ex, int64_t nrb, const int32_t* __restrict__ blkmap, int64_t blkrows) {
     __shared__ unsigned long long smax[8];
     const int tid = threadIdx.x, r8 = tid >> 6, ct = tid & 63;
     const int64_t row = (int64_t)blockIdx.x * 8 + r8;
+    // optional gather: logical row block b (blkrows rows) is read from source block blkmap[b] -- lets the sharded GP slice the
+    // rank-major all-gather buffer straight into stripe order without a reordering copy
+    const int64_t srow = (blkmap != nullptr && row < rows) ? (int64_t)blkmap[row / blkrows] * blkrows + row % blkrows : row;
     if (ct == 0) smax[r8] = 0ull;
     __syncthreads();
     const int64_t nchunks = K / 16;
@@ -51,7 +54,7 @@ oz_slice_kernel(const double* __restrict__ P, int64_t rows, int64_t K, int64_t l
     unsigned long long mb = 0ull;
     if (live)
         for (int64_t c = ct; c < nchunks; c += 64) {
-            const double2* p = reinterpret_cast<const double2*>(P + row * ld + c * 16);
+            const double2* p = reinterpret_cast<const double2*>(P + srow * ld + c * 16);
 #pragma unroll
             for (int i = 0; i < 8; i++) {
                 const double2 v = p[i];
@@ -76,7 +79,7 @@ oz_slice_kernel(const double* __restrict__ P, int64_t rows, int64_t K, int64_t l
 #pragma unroll
         for (int s = 0; s < OZ_S; s++) w[s][0] = w[s][1] = w[s][2] = w[s][3] = 0u;
         if (live && !poisoned) {
-            const double* p = P + row * ld + c * 16;
+            const double* p = P + srow * ld + c * 16;
 #pragma unroll
             for (int i = 0; i < 16; i++) {
                 double x = scalbn(p[i], -e);                              // |x| < 1, exact
@@ -724,12 +727,13 @@ static inline int64_t oz_rows_pad(int64_t rows) { return ((rows + 127) / 128) * 
 int64_t oz_slice_buffer_bytes(int64_t rows, int64_t K) { return oz_rows_pad(rows) * K * OZ_S + oz_rows_pad(rows) * (int64_t)sizeof(double); }
 
 // slices rows x K of P into buf (digits) + exponents stored right behind them
-int oz_slice(Ctx* ctx, const double* P, int64_t rows, int64_t K, int64_t ld, void* buf, cudaStream_t st) {
+int oz_slice(Ctx* ctx, const double* P, int64_t rows, int64_t K, int64_t ld, void* buf, cudaStream_t st, const int32_t* blkmap,
+             int64_t blkrows) {
     if (K % OZ_BK != 0 || (ld & 1) || ((uintptr_t)P & 15)) return BGP_E_ARG;
     const int64_t rp = oz_rows_pad(rows), nrb = rp / 128;
     int8_t* dig = reinterpret_cast<int8_t*>(buf);
     double* ex = reinterpret_cast<double*>(dig + rp * K * OZ_S);
-    oz_slice_kernel<<<(unsigned)(rp / 8), 512, 0, st>>>(P, rows, K, ld, dig, ex, nrb);
+    oz_slice_kernel<<<(unsigned)(rp / 8), 512, 0, st>>>(P, rows, K, ld, dig, ex, nrb, blkmap, blkrows > 0 ? blkrows : 1);
     BGP_LAUNCH_OK(ctx);
     return 0;
 }

@@ -263,7 +263,7 @@ static int launch_leaf(Ctx* ctx, double* A, int64_t lda, int n, double* dinv, in
 }
 
 int64_t oz_slice_buffer_bytes(int64_t rows, int64_t K);
-int oz_slice(Ctx*, const double*, int64_t, int64_t, int64_t, void*, cudaStream_t);
+int oz_slice(Ctx*, const double*, int64_t, int64_t, int64_t, void*, cudaStream_t, const int32_t* blkmap = nullptr, int64_t blkrows = 0);
 int oz_gemm(Ctx*, const void*, int64_t, int64_t, const void*, int64_t, int64_t, int64_t, int64_t, int64_t, double, double*,
             int64_t, int, int64_t, int64_t, cudaStream_t, int tiles_per_cta);
 

@@ -248,6 +248,16 @@ class Engine:
         _lib.check(self.L.bgp_oz_slice(self.h, _ptr(P), rows, K, self._ld(P), _ptr(buf), buf.numel(), self._stream()), "bgp_oz_slice")
         return buf
 
+    def oz_slice_gather(self, P: torch.Tensor, rows: int, blkmap: torch.Tensor, blkrows: int, buf: Optional[torch.Tensor] = None):
+        """Slice ``rows`` logical rows whose block b lives at source block blkmap[b] of P (int32 device tensor)."""
+        K = P.shape[1]
+        need = int(self.L.bgp_oz_slice_bytes(rows, K))
+        if buf is None or buf.numel() < need:
+            buf = torch.empty(need, dtype=torch.uint8, device=self.device)
+        _lib.check(self.L.bgp_oz_slice_gather(self.h, _ptr(P), rows, K, self._ld(P), _ptr(blkmap), blkrows, _ptr(buf), buf.numel(),
+                                              self._stream()), "bgp_oz_slice_gather")
+        return buf
+
     def oz_gemm(self, bufA, rowsA, arow0, bufB, rowsB, brow0, C_, K, alpha=-1.0, tri=False, roff=0, coff=0):
         M, N = C_.shape
         rc = self.L.bgp_oz_gemm(self.h, _ptr(bufA), rowsA, arow0, _ptr(bufB), rowsB, brow0, M, N, K, float(alpha), _ptr(C_),

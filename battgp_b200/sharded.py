@@ -78,6 +78,9 @@ class CudaOps:
     def oz_slice(self, P, buf):
         return self.eng.oz_slice(P, buf)
 
+    def oz_slice_gather(self, P, rows, blkmap, blkrows, buf):
+        return self.eng.oz_slice_gather(P, rows, blkmap, blkrows, buf)
+
     def oz_gemm(self, buf, rows, arow0, brow0, C, K, alpha, tri, roff, coff):
         self.eng.oz_gemm(buf, rows, arow0, buf, rows, brow0, C, K, alpha=alpha, tri=tri, roff=roff, coff=coff)
 
@@ -193,7 +196,11 @@ class ShardedGP:
                     self.rows[i][:, b0k:ek].copy_(send[o:o + self.nbi(i)])
                     o += NB
             t0 = self._tick("panel_trsm", t0)
-            # exchange: every rank ends up with the whole panel, reordered into stripe order
+            # exchange: every rank ends up with the whole panel.  The all-gather result is rank-major; the int8 path
+            # slices it straight into stripe order (block map), the DMMA path needs a reordered fp64 copy.
+            use_oz = getattr(ops, "has_oz", False) and nbk % 64 == 0 and len(mine) > 0
+            panel = None
+            panel_rows = nbelow * NB
             if P > 1:
                 assert send.is_contiguous()
                 recv = torch.empty((P * cnt_max * NB, nbk), dtype=send.dtype, device=send.device)
@@ -201,23 +208,28 @@ class ShardedGP:
                 self.bytes_received += (P - 1) * cnt_max * NB * nbk * 8
                 first = {r: next(j for j in range(k + 1, k + 1 + P) if j % P == r) for r in range(P)}
                 idx = [(j % P) * cnt_max + (j - first[j % P]) // P for j in range(k + 1, self.nblk)]
-                sel = torch.tensor(idx, dtype=torch.long, device=send.device)
-                panel = recv.view(P * cnt_max, NB, nbk).index_select(0, sel).view(-1, nbk)
+                t0 = self._tick("allgather", t0)
+                if not mine:
+                    pass                                     # this rank has no stripe below the panel: nothing to update
+                elif use_oz and hasattr(ops, "oz_slice_gather"):
+                    blkmap = torch.tensor(idx, dtype=torch.int32, device=send.device)
+                    self._ozbuf = ops.oz_slice_gather(recv, panel_rows, blkmap, NB, getattr(self, "_ozbuf", None))
+                else:
+                    sel = torch.tensor(idx, dtype=torch.long, device=send.device)
+                    panel = recv.view(P * cnt_max, NB, nbk).index_select(0, sel).view(-1, nbk)
+                    if use_oz:
+                        self._ozbuf = ops.oz_slice(panel, getattr(self, "_ozbuf", None))
                 del recv
             else:
                 panel = send
-            # trailing update of the owned stripes; with the int8/tcgen05 path the gathered panel is sliced ONCE and
-            # every stripe's product re-uses the digit planes
-            t0 = self._tick("allgather+reorder", t0)
-            use_oz = getattr(ops, "has_oz", False) and nbk % 64 == 0 and len(mine) > 0
-            if use_oz:
-                self._ozbuf = ops.oz_slice(panel, getattr(self, "_ozbuf", None))
-            t0 = self._tick("slice", t0)
+                if use_oz:
+                    self._ozbuf = ops.oz_slice(panel, getattr(self, "_ozbuf", None))
+            t0 = self._tick("reorder+slice", t0)
             for t, i in enumerate(mine):
                 b0i, ei = self.b0(i), self.e(i)
                 C = self.rows[i][:, ek:ei]
                 if use_oz:
-                    ops.oz_gemm(self._ozbuf, panel.shape[0], (i - k - 1) * NB, 0, C, nbk, -1.0, True, b0i, ek)
+                    ops.oz_gemm(self._ozbuf, panel_rows if P > 1 else panel.shape[0], (i - k - 1) * NB, 0, C, nbk, -1.0, True, b0i, ek)
                 else:
                     A = panel[(i - k - 1) * NB:(i - k - 1) * NB + self.nbi(i)]
                     B = panel[:ei - ek]

@@ -117,6 +117,10 @@ int bgp_gemm_nt_i8(bgp_ctx* ctx, int64_t M, int64_t N, int64_t K, double alpha,
  * bgp_oz_gemm : C[M,N] += alpha * A B^T with A = rows arow0.. (multiple of 128) of bufA, B = rows brow0.. (multiple of 64) of bufB. */
 int64_t bgp_oz_slice_bytes(int64_t rows, int64_t K);
 int bgp_oz_slice(bgp_ctx* ctx, const double* P, int64_t rows, int64_t K, int64_t ld, void* buf, int64_t buf_bytes, void* stream);
+/* like bgp_oz_slice, but logical row block b (blkrows rows each) is read from source block blkmap[b] (device int32 array):
+ * slices a rank-major all-gather buffer directly into stripe order (battgp_b200/sharded.py). */
+int bgp_oz_slice_gather(bgp_ctx* ctx, const double* P, int64_t rows, int64_t K, int64_t ld, const int32_t* blkmap, int64_t blkrows,
+                        void* buf, int64_t buf_bytes, void* stream);
 int bgp_oz_gemm(bgp_ctx* ctx, const void* bufA, int64_t rowsA, int64_t arow0, const void* bufB, int64_t rowsB, int64_t brow0,
                 int64_t M, int64_t N, int64_t K, double alpha, double* C, int64_t ldc, int tri, int64_t roff, int64_t coff,
                 void* stream);
