@@ -143,3 +143,24 @@ def test_large_n_properties(eng):
     prior = eng.cov_diag(E.battgp_spec(), xq)
     assert bool((v >= 1e-10).all()) and bool((v <= prior * (1 + 1e-12)).all())
     assert bool(torch.isfinite(m).all())
+
+
+def test_cell_batch_matches_oracle(eng):
+    """battgp_full.py:41-60,100-120: several cells of one battery, shared buffers, one H2D / one D2H."""
+    from battgp_b200 import engine as E
+    from battgp_b200.batch import CellBatch
+    from battgp_b200.synth import synth_field_data
+    sizes = [600, 701, 350]
+    xs, ys, xqs = [], [], []
+    for c, n in enumerate(sizes):
+        x, y = synth_field_data(n, seed=0, cell=c)
+        xs.append(x); ys.append(y); xqs.append(orc.query_grid(x))
+    cb = CellBatch("cuda:0", n_max=800, m_query=300)
+    means, vars_, lmls = cb.run(E.battgp_spec(), 2.33e-6, xs, ys, xqs)
+    assert means.shape == (3, 300) and vars_.shape == (3, 300)
+    for c in range(3):
+        f = orc.fit(orc.battgp_spec(), xs[c], ys[c], 2.33e-6)
+        mr, vr = orc.predict(orc.battgp_spec(), xs[c], f, xqs[c])
+        np.testing.assert_allclose(means[c], mr, rtol=1e-7)
+        np.testing.assert_allclose(vars_[c], vr, rtol=1e-6)
+        assert abs(lmls[c] - f.lml) < 1e-9 * abs(f.lml)
