@@ -53,7 +53,8 @@ static inline int64_t potrf_trsm_scratch_bytes(int64_t n, int64_t nb) {
 // panel width: "nb" knob, or (nb == 0) automatic -- wide panels amortise the fixed per-tile cost of the int8 path
 static inline int64_t effective_nb(const Ctx* ctx, int64_t n) {
     if (ctx->nb > 0) return ctx->nb;
-    return (ctx->ozaki && n >= 30000) ? 2048 : 1024;
+    if (ctx->ozaki && n >= 30000) return 2048;
+    return n < 10000 ? 512 : 1024;          // measured: profiles/probe_r01_potrf_mid_nb_sweep.jsonl
 }
 
 // Right-looking over NB-wide panels with one panel of look-ahead (see potrf.cu header comment).

@@ -272,3 +272,22 @@ if "small" in what:
         ev1.record(); torch.cuda.synchronize()
         print(json.dumps({"op": "small_n_fit_predict", "n": n, "ours_ms": t_ours * 1e3, "torch_cusolver_ms": t_lib * 1e3,
                           "our_potrf_ms": ev0.elapsed_time(ev1) / 5}), flush=True)
+if "midsweep" in what:
+    for n in (6144, 8192, 12288, 16384, 24576):
+        x, y = synth_field_data(n, 0)
+        xd = torch.tensor(x, device=dev); spec = E.battgp_spec()
+        K = E.alloc_matrix(n, n, dev)
+        for nb in (256, 512, 768, 1024, 1536):
+            if n <= 2 * nb: continue
+            eng.set("nb", nb); eng.set("ozaki", 1)
+            best = 1e30
+            for r in range(3):
+                eng.cov_build(spec, xd, noise=2.33e-6, symmetric=True, out=K)
+                torch.cuda.synchronize()
+                e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+                e0.record(); info, ld, dinv = eng.potrf(K); e1.record(); torch.cuda.synchronize()
+                best = min(best, e0.elapsed_time(e1))
+            print(json.dumps({"op": "potrf_mid", "n": n, "nb": nb, "info": info, "ms": round(best, 3)}), flush=True)
+        eng.set("nb", 0)
+        del K
+        torch.cuda.empty_cache()
