@@ -33,19 +33,29 @@ __device__ __forceinline__ double warp_potrf32(double* D, double* rdiag, double*
     for (int k = 0; k < 32; k++) a[k] = (k <= lane) ? D[lane * SP + k] : 0.0;
     double my_d = 1.0;
     int fail = 0;
+    // software-pipelined over the pivots: as soon as column j has updated a[j+1], the next pivot's broadcast and rsqrt
+    // (the long-latency part of the chain) are issued, and the remaining updates of column j run underneath them
+    double d = shfl_d(a[0], 0);
+    double rinv = rsqrt(d);
 #pragma unroll
     for (int j = 0; j < 32; j++) {
-        const double d = shfl_d(a[j], j);
         if (!(d > 0.0) && fail == 0) fail = j + 1;
-        const double rinv = rsqrt(d);
         const double l = (lane == j) ? d * rinv : a[j] * rinv;
         a[j] = l;
         if (lane == j) { my_d = d; rdiag[j] = rinv; }
         // broadcast the column through shared memory: every lane then reads l_k with one (conflict-free, broadcast) LDS.64
         colbuf[(j & 1) * 32 + lane] = l;
         __syncwarp();
+        double d_next = 1.0, rinv_next = 1.0;
+        if (j + 1 < 32) {
+            a[j + 1] = fma(-l, colbuf[(j & 1) * 32 + j + 1], a[j + 1]);
+            d_next = shfl_d(a[j + 1], j + 1);
+            rinv_next = rsqrt(d_next);
+        }
 #pragma unroll
-        for (int k = j + 1; k < 32; k++) a[k] = fma(-l, colbuf[(j & 1) * 32 + k], a[k]);
+        for (int k = j + 2; k < 32; k++) a[k] = fma(-l, colbuf[(j & 1) * 32 + k], a[k]);
+        d = d_next;
+        rinv = rinv_next;
     }
     *bad = fail;
 #pragma unroll
