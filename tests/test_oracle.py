@@ -136,3 +136,28 @@ def test_psd_safe_cholesky_jitter_sequence():
     assert jit in (1e-8, 1e-7, 1e-6)
     with pytest.raises(np.linalg.LinAlgError):
         orc.psd_safe_cholesky(-np.eye(4))
+
+
+REAL = np.load(os.path.join(os.path.dirname(__file__), "golden", "real_field_data.npz")) \
+    if os.path.exists(os.path.join(os.path.dirname(__file__), "golden", "real_field_data.npz")) else None
+REAL_KEYS = ("b14_c1", "b14_cpack", "b3_c5")
+
+
+@pytest.mark.parametrize("key", REAL_KEYS)
+def test_real_field_data_fixture_is_reproducible(key):
+    """tests/golden/real_field_data.npz holds training sets produced by the reference's own data layer
+    (batt_data.py:180-256 generateTrainingData on tests/data/cache/*.feather) plus the oracle's results on them; the
+    committed results must be what the oracle computes today, and the data must look like BattGP's (4 columns
+    age/I/SOC/T, ages sorted, R > 0, every op-point feature inside the reference's filter ranges)."""
+    assert REAL is not None
+    x, y, xq = REAL[f"{key}_x"], REAL[f"{key}_y"], REAL[f"{key}_xq"]
+    assert x.shape[1] == 4 and x.shape[0] == y.shape[0] and xq.shape == (300, 4)
+    assert np.all(np.diff(x[:, 0]) >= 0) and np.all(np.isfinite(x)) and np.all(np.isfinite(y))
+    th = REAL["theta"]
+    spec = orc.battgp_spec(th[1], th[2], th[3:6])
+    f = orc.fit(spec, x, y, th[0])
+    mean, var = orc.predict(spec, x, f, xq)
+    assert f.jitter == float(REAL[f"{key}_jitter"])
+    assert abs(f.lml - float(REAL[f"{key}_lml"])) < 1e-9 * abs(f.lml)
+    np.testing.assert_allclose(mean, REAL[f"{key}_mean"], rtol=1e-8)
+    np.testing.assert_allclose(var, REAL[f"{key}_var"], rtol=1e-6)
