@@ -3,6 +3,7 @@
 #include <cmath>
 #include <cstring>
 #include <new>
+#include <vector>
 #include "common.cuh"
 
 namespace bgp {
@@ -45,16 +46,51 @@ struct DeviceGuard {
     ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
 };
 
-// scratch for the int8 path of the panel TRSM: X1 [n - nb, nb/2] and L21 [nb/2, nb/2] digit planes
-static inline int64_t potrf_trsm_scratch_bytes(int64_t n, int64_t nb) {
-    return ((oz_slice_buffer_bytes(n - nb, nb / 2) + 255) / 256) * 256 + ((oz_slice_buffer_bytes(nb / 2, nb / 2) + 255) / 256) * 256;
+// Panel schedule of the look-ahead factorisation.  Panel k covers columns [start[k], start[k+1]).  With the "nb" knob set
+// every panel has that width; otherwise the width follows the rows still to be factorised (m = R - start[k]): wide panels
+// while the trailing update is long enough to hide the panel chain behind it (and wide K amortises the fixed per-tile cost
+// of the int8 path), narrower ones once the chain  diag-block -> panel TRSM -> next column block  is what is exposed.
+struct PanelSchedule {
+    std::vector<int64_t> start;      // npanels + 1 entries
+    int64_t ozbytes = 0;             // one digit-plane buffer for the rows below a panel (int8 path)
+    int64_t trsm_bytes = 0;          // scratch of the int8 path inside the panel TRSM
+    int64_t npanels() const { return (int64_t)start.size() - 1; }
+    int64_t width(int64_t k) const { return start[k + 1] - start[k]; }
+};
+
+static inline int64_t panel_width(const Ctx* ctx, int64_t m, int64_t idx) {
+    if (ctx->nb > 0) return ctx->nb;
+    int64_t w = (m >= ctx->sched_t1024) ? 1024 : 512;
+    if (ctx->ozaki) {
+        if (ctx->sched_t2048 > 0 && m >= ctx->sched_t2048) w = 2048;
+        if (ctx->sched_t4096 > 0 && m >= ctx->sched_t4096) w = 4096;
+    }
+    if (idx == 0 && ctx->sched_w0 > 0 && w > ctx->sched_w0) w = ctx->sched_w0;
+    if (idx == 1 && ctx->sched_w1 > 0 && w > ctx->sched_w1) w = ctx->sched_w1;
+    return w;
 }
 
-// panel width: "nb" knob, or (nb == 0) automatic -- wide panels amortise the fixed per-tile cost of the int8 path
-static inline int64_t effective_nb(const Ctx* ctx, int64_t n) {
-    if (ctx->nb > 0) return ctx->nb;
-    if (ctx->ozaki && n >= 30000) return 2048;
-    return n < 10000 ? 512 : 1024;          // measured: profiles/probe_r01_potrf_mid_nb_sweep.jsonl
+static inline int64_t round256(int64_t b) { return ((b + 255) / 256) * 256; }
+
+// R rows (n of them the symmetric matrix, the rest ride along), n columns
+static void make_schedule(const Ctx* ctx, int64_t R, int64_t n, PanelSchedule& s) {
+    s.start.clear();
+    s.ozbytes = s.trsm_bytes = 0;
+    for (int64_t k0 = 0, idx = 0; k0 < n; idx++) {
+        int64_t w = panel_width(ctx, R - k0, idx);
+        if (w > n - k0) w = n - k0;
+        s.start.push_back(k0);
+        k0 += w;
+        const int64_t below = R - k0;
+        if (below > 0 && w % 64 == 0) {
+            const int64_t ob = round256(oz_slice_buffer_bytes(below, w));
+            // X1 [below, w/2] and L21 [w/2, w/2] digit planes (top split of trsm_rlt_rec; deeper levels are smaller)
+            const int64_t tb = round256(oz_slice_buffer_bytes(below, w / 2)) + round256(oz_slice_buffer_bytes(w / 2, w / 2));
+            if (k0 < n && ob > s.ozbytes) s.ozbytes = ob;      // the last panel is never sliced
+            if (tb > s.trsm_bytes) s.trsm_bytes = tb;
+        }
+    }
+    s.start.push_back(n);
 }
 
 // Right-looking over NB-wide panels with one panel of look-ahead (see potrf.cu header comment).
@@ -64,8 +100,10 @@ static inline int64_t effective_nb(const Ctx* ctx, int64_t n) {
 // recursive TRSM).
 static int potrf_driver(Ctx* ctx, double* A, int64_t n, int64_t mx, int64_t lda, double* dinv, cudaStream_t mainst) {
     const int64_t R = n + mx;
-    const int64_t NB = effective_nb(ctx, R);
-    if (!ctx->lookahead || n <= 2 * NB) {
+    PanelSchedule S;
+    make_schedule(ctx, R, n, S);
+    const int64_t npanels = S.npanels();
+    if (!ctx->lookahead || npanels <= 2) {
         int rc = potrf_rec(ctx, A, n, lda, dinv, 0, mainst);
         if (!rc && mx > 0) rc = trsm_rlt_rec(ctx, A, n, lda, dinv, A + n * lda, mx, lda, mainst);
         return rc;
@@ -73,9 +111,10 @@ static int potrf_driver(Ctx* ctx, double* A, int64_t n, int64_t mx, int64_t lda,
     cudaStream_t P = ctx->panel_stream;
     // int8/tcgen05 trailing updates (ozaki.cu): two slice buffers (panel k is still being read by T_k on the caller's
     // stream while panel k+1 is sliced on the panel stream)
-    const int64_t ozbytes = ((oz_slice_buffer_bytes(R - NB, NB) + 255) / 256) * 256;
-    const bool oz = ctx->ozaki && ctx->ws && (NB % 64 == 0) && ((lda & 1) == 0) && (((uintptr_t)A & 15) == 0) &&
-                    (((uintptr_t)ctx->ws & 255) == 0) && ctx->ws_bytes >= 2 * ozbytes;
+    const int64_t ozbytes = S.ozbytes;
+    bool oz = ctx->ozaki && ctx->ws && ((lda & 1) == 0) && (((uintptr_t)A & 15) == 0) && (((uintptr_t)ctx->ws & 255) == 0) &&
+              ozbytes > 0 && ctx->ws_bytes >= 2 * ozbytes;
+    for (int64_t k = 0; oz && k + 1 < npanels; k++) oz = (S.width(k) % 64 == 0);
     void* ozbuf[2] = {ctx->ws, reinterpret_cast<char*>(ctx->ws) + ozbytes};
     // the panel TRSM (stream P) gets its own scratch behind the two panel buffers
     struct TrsmScratch {
@@ -86,10 +125,10 @@ static int potrf_driver(Ctx* ctx, double* A, int64_t n, int64_t mx, int64_t lda,
                    (oz && ctx->ws_bytes > 2 * ozbytes) ? ctx->ws_bytes - 2 * ozbytes : 0);
     BGP_CUDA_OK(cudaEventRecord(ctx->ev_fork, mainst));
     BGP_CUDA_OK(cudaStreamWaitEvent(P, ctx->ev_fork, 0));
-    const int64_t npanels = (n + NB - 1) / NB;
     for (int64_t k = 0; k < npanels; k++) {
-        const int64_t k0 = k * NB;
-        const int64_t nbk = (n - k0 < NB) ? n - k0 : NB;
+        const int64_t k0 = S.start[k];
+        const int64_t nbk = S.width(k);
+        const int64_t wprev = k >= 1 ? S.width(k - 1) : 0;
         const int64_t below = R - k0 - nbk;                    // rows under the diagonal block, extra rows included
         double* Akk = A + k0 * lda + k0;
         double* dinv_k = dinv + (k0 / LEAF) * (int64_t)LEAF * LEAF;
@@ -99,24 +138,26 @@ static int potrf_driver(Ctx* ctx, double* A, int64_t n, int64_t mx, int64_t lda,
             if (k >= 2) BGP_CUDA_OK(cudaStreamWaitEvent(P, ctx->ev_trail[(k - 2) % 3], 0));
             if (oz) {
                 // panel k-1 was sliced (rows k0.. of it are rows 0.. of its slice buffer)
-                if ((rc = oz_gemm(ctx, ozbuf[(k - 1) & 1], R - k0, 0, ozbuf[(k - 1) & 1], R - k0, 0, R - k0, nbk, NB, -1.0, Akk, lda,
+                if ((rc = oz_gemm(ctx, ozbuf[(k - 1) & 1], R - k0, 0, ozbuf[(k - 1) & 1], R - k0, 0, R - k0, nbk, wprev, -1.0, Akk, lda,
                                   1, 0, 0, P, ctx->oz_tpc))) return rc;
             } else {
-                const double* Lp = A + k0 * lda + (k0 - NB);     // rows k0.., columns of panel k-1
-                GemmArgs g{Lp, lda, Lp, lda, Akk, lda, (int)(R - k0), (int)nbk, (int)NB, -1.0, 1.0, 1, 0, 0};
+                const double* Lp = A + k0 * lda + (k0 - wprev);  // rows k0.., columns of panel k-1
+                GemmArgs g{Lp, lda, Lp, lda, Akk, lda, (int)(R - k0), (int)nbk, (int)wprev, -1.0, 1.0, 1, 0, 0};
                 if ((rc = gemm_nt(ctx, g, P))) return rc;
             }
         }
         if ((rc = potrf_rec(ctx, Akk, nbk, lda, dinv_k, k0, P))) return rc;
         if (below > 0 && (rc = trsm_rlt_rec(ctx, Akk, nbk, lda, dinv_k, Akk + nbk * lda, below, lda, P))) return rc;
-        const int64_t t0 = k0 + nbk + NB;
-        if (oz && t0 - NB < n && below > 0 && nbk == NB && (rc = oz_slice(ctx, Akk + nbk * lda, below, nbk, lda, ozbuf[k & 1], P))) return rc;
+        // digit planes of the rows below: read by the column-block update of P_k+1 and by T_k
+        if (oz && k + 1 < npanels && below > 0 && (rc = oz_slice(ctx, Akk + nbk * lda, below, nbk, lda, ozbuf[k & 1], P))) return rc;
         BGP_CUDA_OK(cudaEventRecord(ctx->ev_panel[k % 2], P));
         // ---- T_k (caller's stream): rank-nbk update of everything right of column block k+1
-        if (t0 < n) {
+        if (k + 2 < npanels) {
+            const int64_t t0 = S.start[k + 2];
+            const int64_t wnext = S.width(k + 1);
             BGP_CUDA_OK(cudaStreamWaitEvent(mainst, ctx->ev_panel[k % 2], 0));
             if (oz) {
-                if ((rc = oz_gemm(ctx, ozbuf[k & 1], below, NB, ozbuf[k & 1], below, NB, R - t0, n - t0, nbk, -1.0,
+                if ((rc = oz_gemm(ctx, ozbuf[k & 1], below, wnext, ozbuf[k & 1], below, wnext, R - t0, n - t0, nbk, -1.0,
                                   A + t0 * lda + t0, lda, 1, 0, 0, mainst, ctx->oz_tpc))) return rc;
             } else {
                 const double* Lt = A + t0 * lda + k0;
@@ -207,6 +248,15 @@ int bgp_ctx_set(bgp_ctx* p, const char* key, int value) {
         return 0;
     }
     if (!strcmp(key, "lookahead")) { c->lookahead = value ? 1 : 0; return 0; }
+    if (!strncmp(key, "sched_", 6)) {
+        if (value < 0 || (!strncmp(key, "sched_w", 7) && value % LEAF != 0)) return BGP_E_ARG;
+        if (!strcmp(key, "sched_t1024")) { c->sched_t1024 = value; return 0; }
+        if (!strcmp(key, "sched_t2048")) { c->sched_t2048 = value; return 0; }
+        if (!strcmp(key, "sched_t4096")) { c->sched_t4096 = value; return 0; }
+        if (!strcmp(key, "sched_w0")) { c->sched_w0 = value; return 0; }
+        if (!strcmp(key, "sched_w1")) { c->sched_w1 = value; return 0; }
+        return BGP_E_ARG;
+    }
     if (!strcmp(key, "ozaki")) { c->ozaki = value ? 1 : 0; return 0; }
     if (!strcmp(key, "oz_cluster")) { if (value != 1 && value != 2 && value != 4) return BGP_E_ARG; c->oz_cluster = value; return 0; }
     if (!strcmp(key, "oz_tpc")) { if (value < 0 || value > 4096) return BGP_E_ARG; c->oz_tpc = value; return 0; }
@@ -217,9 +267,11 @@ int bgp_ctx_set(bgp_ctx* p, const char* key, int value) {
 int64_t bgp_potrf_workspace_bytes(const bgp_ctx* p, int64_t n) {
     if (!p || n <= 0) return 0;
     const Ctx* c = reinterpret_cast<const Ctx*>(p);
-    const int64_t nb = effective_nb(c, n);
-    if (n <= 2 * nb) return 0;
-    return 2 * (((oz_slice_buffer_bytes(n - nb, nb) + 255) / 256) * 256) + potrf_trsm_scratch_bytes(n, nb);
+    // n counts every row (augmented ones included): the schedule of an [n, n - mx] factorisation is a prefix of this one
+    PanelSchedule S;
+    make_schedule(c, n, n, S);
+    if (S.npanels() <= 2) return 0;
+    return 2 * S.ozbytes + S.trsm_bytes;
 }
 
 int bgp_ctx_set_workspace(bgp_ctx* p, void* ptr, int64_t bytes) {

@@ -19,8 +19,14 @@ struct Ctx {
     int32_t* d_info = nullptr;              // first failing pivot (1-based), INT_MAX when none
     double* d_scal = nullptr;               // [0] logdet accumulator, [1] dot result, [8..] dot partials
     double* d_scratch = nullptr;            // SCRATCH_BYTES of reduction partials (lml_grad)
-    int nb = 0;                             // 0 = automatic (api.cu effective_nb)
+    int nb = 0;                             // 0 = automatic schedule (api.cu panel_width), else uniform panel width
     int lookahead = 1;
+    // automatic panel schedule (nb == 0): the width of a panel follows the rows still to be factorised (api.cu panel_width)
+    int sched_t1024 = 9000;                 // remaining rows >= this: 1024-wide panels (else 512)
+    int sched_t2048 = 17000;                // int8 path only: 2048-wide panels from here up (0 = never)
+    int sched_t4096 = 0;                    // int8 path only: 4096-wide panels from here up (0 = never)
+    int sched_w0 = 0;                       // cap on the width of the first panel (its chain has nothing to hide behind)
+    int sched_w1 = 0;                       // cap on the width of the second panel
     int oz_cluster = 2;                     // CTAs per cluster sharing the A operand by multicast (1, 2 or 4) when fully persistent
     int oz_tpc = 2;                         // tiles per CTA of the int8 kernel inside bgp_potrf (0 = fully persistent)
     int ozaki = 0;                          // 1: big trailing updates of bgp_potrf go through the int8/tcgen05 path

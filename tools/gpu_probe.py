@@ -291,3 +291,36 @@ if "midsweep" in what:
         eng.set("nb", 0)
         del K
         torch.cuda.empty_cache()
+if "sched" in what:
+    # panel-schedule sweep: uniform widths ("nb") against the remaining-rows rule (sched_* knobs of bgp_ctx_set)
+    spec = E.battgp_spec()
+    DEF = {"sched_t1024": 9000, "sched_t2048": 17000, "sched_t4096": 0, "sched_w0": 0, "sched_w1": 0}
+    def run(n, xd, K, cfg, reps=2):
+        for k, v in DEF.items(): eng.set(k, cfg.get(k, v))
+        eng.set("nb", cfg.get("nb", 0)); eng.set("ozaki", 1)
+        best = 1e30
+        for r in range(reps):
+            eng.cov_build(spec, xd, noise=2.33e-6, symmetric=True, out=K)
+            torch.cuda.synchronize()
+            e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+            e0.record(); info, ld, dinv = eng.potrf(K); e1.record(); torch.cuda.synchronize()
+            best = min(best, e0.elapsed_time(e1))
+        print(json.dumps({"op": "potrf_sched", "n": n, "cfg": cfg, "info": info, "logdet": ld, "ms": round(best, 3)}), flush=True)
+    sweeps = {
+        40000: [{"nb": 2048}, {}, {"sched_t2048": 10000}, {"sched_t2048": 18000}, {"sched_t2048": 22000},
+                {"sched_t1024": 6000}, {"sched_t1024": 12000}, {"sched_w0": 512}, {"sched_w0": 1024},
+                {"sched_w0": 1024, "sched_t4096": 30000}, {"sched_w0": 1024, "sched_w1": 2048, "sched_t4096": 26000},
+                {"sched_w0": 1024, "sched_w1": 2048, "sched_t4096": 22000}, {"sched_w0": 1024, "sched_t2048": 18000, "sched_t1024": 12000}],
+        24576: [{"nb": 1024}, {"nb": 2048}, {}, {"sched_t2048": 18000}, {"sched_w0": 1024}, {"sched_w0": 512}],
+        16384: [{"nb": 1024}, {"nb": 512}, {}, {"sched_t2048": 0}, {"sched_t2048": 0, "sched_t1024": 12000}, {"sched_w0": 512}, {"sched_w0": 1024}],
+        12288: [{"nb": 512}, {"nb": 1024}, {}, {"sched_t1024": 6000}, {"sched_t1024": 12000}],
+        8192: [{"nb": 512}, {}, {"sched_t1024": 6000}],
+    }
+    for n, cfgs in sweeps.items():
+        x, y = synth_field_data(n, 0)
+        xd = torch.tensor(x, device=dev)
+        K = E.alloc_matrix(n, n, dev)
+        for cfg in cfgs: run(n, xd, K, cfg)
+        del K
+    for k, v in DEF.items(): eng.set(k, v)
+    eng.set("nb", 0)
