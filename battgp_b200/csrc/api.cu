@@ -1,6 +1,7 @@
 // extern "C" surface of libbattgp_b200.so (include/battgp_b200.h) and the look-ahead Cholesky driver.
 #include <climits>
 #include <cmath>
+#include <cstdio>
 #include <cstring>
 #include <new>
 #include <vector>
@@ -125,6 +126,16 @@ static int potrf_driver(Ctx* ctx, double* A, int64_t n, int64_t mx, int64_t lda,
                    (oz && ctx->ws_bytes > 2 * ozbytes) ? ctx->ws_bytes - 2 * ozbytes : 0);
     BGP_CUDA_OK(cudaEventRecord(ctx->ev_fork, mainst));
     BGP_CUDA_OK(cudaStreamWaitEvent(P, ctx->ev_fork, 0));
+    // "trace" knob: timed events around every P_k / T_k, printed to stderr after the factorisation (diagnostics only)
+    std::vector<cudaEvent_t> tev;
+    auto mark = [&](cudaStream_t s) {
+        if (!ctx->trace) return;
+        cudaEvent_t e;
+        cudaEventCreate(&e);
+        cudaEventRecord(e, s);
+        tev.push_back(e);
+    };
+    mark(mainst);
     for (int64_t k = 0; k < npanels; k++) {
         const int64_t k0 = S.start[k];
         const int64_t nbk = S.width(k);
@@ -134,6 +145,7 @@ static int potrf_driver(Ctx* ctx, double* A, int64_t n, int64_t mx, int64_t lda,
         double* dinv_k = dinv + (k0 / LEAF) * (int64_t)LEAF * LEAF;
         int rc;
         // ---- P_k (panel stream): bring column block k up to date with panel k-1, factor it, solve the rows below
+        mark(P);
         if (k >= 1) {
             if (k >= 2) BGP_CUDA_OK(cudaStreamWaitEvent(P, ctx->ev_trail[(k - 2) % 3], 0));
             if (oz) {
@@ -146,16 +158,21 @@ static int potrf_driver(Ctx* ctx, double* A, int64_t n, int64_t mx, int64_t lda,
                 if ((rc = gemm_nt(ctx, g, P))) return rc;
             }
         }
+        mark(P);
         if ((rc = potrf_rec(ctx, Akk, nbk, lda, dinv_k, k0, P))) return rc;
+        mark(P);
         if (below > 0 && (rc = trsm_rlt_rec(ctx, Akk, nbk, lda, dinv_k, Akk + nbk * lda, below, lda, P))) return rc;
+        mark(P);
         // digit planes of the rows below: read by the column-block update of P_k+1 and by T_k
         if (oz && k + 1 < npanels && below > 0 && (rc = oz_slice(ctx, Akk + nbk * lda, below, nbk, lda, ozbuf[k & 1], P))) return rc;
         BGP_CUDA_OK(cudaEventRecord(ctx->ev_panel[k % 2], P));
+        mark(P);
         // ---- T_k (caller's stream): rank-nbk update of everything right of column block k+1
         if (k + 2 < npanels) {
             const int64_t t0 = S.start[k + 2];
             const int64_t wnext = S.width(k + 1);
             BGP_CUDA_OK(cudaStreamWaitEvent(mainst, ctx->ev_panel[k % 2], 0));
+            mark(mainst);
             if (oz) {
                 if ((rc = oz_gemm(ctx, ozbuf[k & 1], below, wnext, ozbuf[k & 1], below, wnext, R - t0, n - t0, nbk, -1.0,
                                   A + t0 * lda + t0, lda, 1, 0, 0, mainst, ctx->oz_tpc))) return rc;
@@ -165,10 +182,24 @@ static int potrf_driver(Ctx* ctx, double* A, int64_t n, int64_t mx, int64_t lda,
                 if ((rc = gemm_nt(ctx, g, mainst))) return rc;
             }
             BGP_CUDA_OK(cudaEventRecord(ctx->ev_trail[k % 3], mainst));
-        }
+            mark(mainst);
+        } else if (ctx->trace) { mark(mainst); mark(mainst); }
     }
     BGP_CUDA_OK(cudaEventRecord(ctx->ev_join, P));
     BGP_CUDA_OK(cudaStreamWaitEvent(mainst, ctx->ev_join, 0));
+    if (ctx->trace) {
+        // per panel: 5 marks on P (start, after column-block update, after diag, after TRSM, after slice) + 2 on main (T_k)
+        BGP_CUDA_OK(cudaStreamSynchronize(mainst));
+        auto at = [&](size_t i) { float ms = 0.f; cudaEventElapsedTime(&ms, tev[0], tev[i]); return ms; };
+        for (int64_t k = 0; k < npanels; k++) {
+            const size_t b = 1 + 7 * (size_t)k;
+            fprintf(stderr, "{\"potrf_trace\": %lld, \"w\": %lld, \"P_start\": %.3f, \"colupd\": %.3f, \"diag\": %.3f, \"trsm\": %.3f, "
+                            "\"slice\": %.3f, \"P_end\": %.3f, \"T_start\": %.3f, \"T_end\": %.3f}\n",
+                    (long long)k, (long long)S.width(k), at(b), at(b + 1) - at(b), at(b + 2) - at(b + 1), at(b + 3) - at(b + 2),
+                    at(b + 4) - at(b + 3), at(b + 4), at(b + 5), at(b + 6));
+        }
+        for (auto e : tev) cudaEventDestroy(e);
+    }
     return 0;
 }
 
@@ -248,6 +279,7 @@ int bgp_ctx_set(bgp_ctx* p, const char* key, int value) {
         return 0;
     }
     if (!strcmp(key, "lookahead")) { c->lookahead = value ? 1 : 0; return 0; }
+    if (!strcmp(key, "trace")) { c->trace = value ? 1 : 0; return 0; }
     if (!strncmp(key, "sched_", 6)) {
         if (value < 0 || (!strncmp(key, "sched_w", 7) && value % LEAF != 0)) return BGP_E_ARG;
         if (!strcmp(key, "sched_t1024")) { c->sched_t1024 = value; return 0; }

@@ -21,6 +21,7 @@ struct Ctx {
     double* d_scratch = nullptr;            // SCRATCH_BYTES of reduction partials (lml_grad)
     int nb = 0;                             // 0 = automatic schedule (api.cu panel_width), else uniform panel width
     int lookahead = 1;
+    int trace = 0;                          // 1: bgp_potrf prints per-panel event timings to stderr (diagnostics)
     // automatic panel schedule (nb == 0): the width of a panel follows the rows still to be factorised (api.cu panel_width)
     int sched_t1024 = 9000;                 // remaining rows >= this: 1024-wide panels (else 512)
     int sched_t2048 = 17000;                // int8 path only: 2048-wide panels from here up (0 = never)

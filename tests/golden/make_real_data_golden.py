@@ -46,5 +46,56 @@ def main():
     print("wrote real_field_data.npz", {k: v.shape for k, v in out.items() if k.endswith("_x")})
 
 
+def main_full(n_max=40000, block=4000):
+    """BASELINE config 2's real-data variant: every filtered row of system 14, cell 1, capped at 40 000,
+    with the oracle's results at FULL size (K assembled row-block by row-block to stay inside host RAM, LAPACK dpotrf in
+    place: ~1-2 min on 8 cores, 13 GB).  Writes real_field_data_40k.npz."""
+    import scipy.linalg as sla
+    cfg.PATH_DATA_CACHE = pathlib.Path(REF) / "tests" / "data" / "cache"
+    cfg.PATH_FIELDDATA_DATA = "<not needed: cache hit>"
+    ocv = read_cell_characteristics(pathlib.Path(REF) / "tests" / "data" / "ocv_linear_approx.csv")
+    bd = BattData("14", ocv)
+    x, y = bd.generateTrainingData(1, max_training_data=n_max, max_age=None)
+    x = np.ascontiguousarray(np.asarray(x, dtype=np.float64))
+    y = np.ascontiguousarray(np.asarray(y, dtype=np.float64).reshape(-1))
+    n = y.shape[0]
+    print("rows", n, "age", bd.age, flush=True)
+    spec = orc.battgp_spec(cfg.OUTPUTSCALE_WIENER, cfg.OUTPUTSCALE_RBF, cfg.LENGTHSCALE_RBF)
+    noise = float(cfg.NOISE_VARIANCE[0])
+    import torch
+    k = np.empty((n, n))
+    for b0 in range(0, n, block):
+        e = min(n, b0 + block)
+        k[b0:e, :] = orc.cov(spec, x[b0:e], x)
+    k[np.diag_indices_from(k)] += noise
+    # torch's LAPACK (scipy's OpenBLAS dpotrf crashes at this size in this container); same dpotrf algorithm, fp64
+    kt = torch.from_numpy(k)
+    ct, info = torch.linalg.cholesky_ex(kt)
+    assert int(info) == 0, int(info)              # no jitter needed on this set
+    del kt, k
+    c = ct.numpy()
+    yt = torch.from_numpy(y).reshape(-1, 1)
+    z = torch.linalg.solve_triangular(ct, yt, upper=False)
+    alpha = torch.linalg.solve_triangular(ct.T, z, upper=True).reshape(-1).numpy()
+    z = z.reshape(-1).numpy()
+    logdet = 2.0 * np.log(np.diag(c)).sum()
+    lml = -0.5 * float(z @ z) - 0.5 * logdet - 0.5 * n * np.log(2.0 * np.pi)
+    t = np.linspace(x[0, 0], bd.age, 300)
+    xq = np.column_stack([t, np.full(300, -15.0), np.full(300, 90.0), np.full(300, 25.0)])
+    kq = orc.cov(spec, xq, x)
+    mean = kq @ alpha
+    v = torch.linalg.solve_triangular(ct, torch.from_numpy(np.ascontiguousarray(kq.T)), upper=False).numpy()
+    var = np.maximum(orc.cov_diag(spec, xq) - (v * v).sum(axis=0), 1e-10)
+    # leading 2048 x 2048 block of L and a strided sample of alpha: direct checks of the factor at full size
+    np.savez_compressed(os.path.join(HERE, "real_field_data_40k.npz"), x=x, y=y, xq=xq, mean=mean, var=var,
+                        lml=np.array(lml), logdet=np.array(logdet), alpha_sample=alpha[::97].copy(),
+                        l_diag=np.diag(c).copy(), l_last_row=c[-1, :].copy(),
+                        theta=np.array([noise, cfg.OUTPUTSCALE_WIENER, cfg.OUTPUTSCALE_RBF, *cfg.LENGTHSCALE_RBF]))
+    print("lml", lml, "logdet", logdet, "mean[:3]", mean[:3], "var[:3]", var[:3], flush=True)
+
+
 if __name__ == "__main__":
-    main()
+    if "--full" in sys.argv:
+        main_full()
+    else:
+        main()

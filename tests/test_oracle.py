@@ -161,3 +161,17 @@ def test_real_field_data_fixture_is_reproducible(key):
     assert abs(f.lml - float(REAL[f"{key}_lml"])) < 1e-9 * abs(f.lml)
     np.testing.assert_allclose(mean, REAL[f"{key}_mean"], rtol=1e-8)
     np.testing.assert_allclose(var, REAL[f"{key}_var"], rtol=1e-6)
+
+
+def test_full_size_real_fixture_leading_block_is_reproducible():
+    """real_field_data_40k.npz (all 40 000 filtered rows of system 14 / cell 1, oracle results from a one-off LAPACK run on
+    the build host): the leading principal block of L depends only on the leading block of K, so the oracle at n0 = 1500
+    must reproduce the stored diagonal of the full-size factor; logdet must equal 2 sum log diag."""
+    R = np.load(os.path.join(os.path.dirname(__file__), "golden", "real_field_data_40k.npz"))
+    x, y, th = R["x"], R["y"], R["theta"]
+    assert x.shape == (40000, 4) and y.shape == (40000,) and np.all(np.diff(x[:, 0]) >= 0)
+    assert abs(2.0 * np.log(R["l_diag"]).sum() - float(R["logdet"])) < 1e-6
+    n0 = 1500
+    spec = orc.battgp_spec(th[1], th[2], th[3:6])
+    L = orc.cholesky_lower(orc.train_cov(spec, x[:n0], th[0]))
+    np.testing.assert_allclose(np.diag(L), R["l_diag"][:n0], rtol=1e-9)

@@ -324,3 +324,20 @@ if "sched" in what:
         del K
     for k, v in DEF.items(): eng.set(k, v)
     eng.set("nb", 0)
+if "trace" in what:
+    # per-panel timeline of the look-ahead factorisation ("trace" knob; lines go to stderr)
+    spec = E.battgp_spec()
+    for n in (40000, 16384):
+        x, y = synth_field_data(n, 0)
+        xd = torch.tensor(x, device=dev)
+        K = E.alloc_matrix(n, n, dev)
+        eng.set("ozaki", 1)
+        for tr in (0, 1):
+            eng.cov_build(spec, xd, noise=2.33e-6, symmetric=True, out=K)
+            torch.cuda.synchronize()
+            eng.set("trace", tr)
+            e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+            e0.record(); info, ld, dinv = eng.potrf(K); e1.record(); torch.cuda.synchronize()
+            eng.set("trace", 0)
+            print(json.dumps({"op": "potrf_trace_total", "n": n, "trace": tr, "ms": e0.elapsed_time(e1)}), flush=True)
+        del K
