@@ -101,6 +101,14 @@ static void make_schedule(const Ctx* ctx, int64_t R, int64_t n, PanelSchedule& s
 // recursive TRSM).
 static int potrf_driver(Ctx* ctx, double* A, int64_t n, int64_t mx, int64_t lda, double* dinv, cudaStream_t mainst) {
     const int64_t R = n + mx;
+    // programmatic dependent launch of the leaf / DMMA GEMM chain pays off while the factorisation is latency-bound
+    // (profiles/probe_r01_pdl.jsonl: N=4096 -4 %, N=8192 -2 %, N>=16384 +0.5 %)
+    struct PdlChain {
+        Ctx* c;
+        int prev;
+        PdlChain(Ctx* c_, bool on) : c(c_), prev(c_->pdl_chain) { c->pdl_chain = on ? 1 : 0; }
+        ~PdlChain() { c->pdl_chain = prev; }
+    } pdl_chain(ctx, R < 12000);
     PanelSchedule S;
     make_schedule(ctx, R, n, S);
     const int64_t npanels = S.npanels();
@@ -280,6 +288,7 @@ int bgp_ctx_set(bgp_ctx* p, const char* key, int value) {
     }
     if (!strcmp(key, "lookahead")) { c->lookahead = value ? 1 : 0; return 0; }
     if (!strcmp(key, "trace")) { c->trace = value ? 1 : 0; return 0; }
+    if (!strcmp(key, "pdl")) { c->pdl = value ? 1 : 0; return 0; }
     if (!strncmp(key, "sched_", 6)) {
         if (value < 0 || (!strncmp(key, "sched_w", 7) && value % LEAF != 0)) return BGP_E_ARG;
         if (!strcmp(key, "sched_t1024")) { c->sched_t1024 = value; return 0; }

@@ -21,6 +21,8 @@ struct Ctx {
     double* d_scratch = nullptr;            // SCRATCH_BYTES of reduction partials (lml_grad)
     int nb = 0;                             // 0 = automatic schedule (api.cu panel_width), else uniform panel width
     int lookahead = 1;
+    int pdl = 1;                            // 1: chain kernels (triangular sweeps, leaf, DMMA GEMMs) use programmatic dependent launch
+    int pdl_chain = 1;                      // leaf/GEMM launches only: cleared by bgp_potrf for large matrices (measured neutral to -0.5 %)
     int trace = 0;                          // 1: bgp_potrf prints per-panel event timings to stderr (diagnostics)
     // automatic panel schedule (nb == 0): the width of a panel follows the rows still to be factorised (api.cu panel_width)
     int sched_t1024 = 9000;                 // remaining rows >= this: 1024-wide panels (else 512)
@@ -53,6 +55,27 @@ void set_error(const char* what, cudaError_t e);
         cudaError_t e__ = cudaGetLastError();                                               \
         if (e__ != cudaSuccess) { ::bgp::set_error("kernel launch", e__); return BGP_E_CUDA; } \
     } while (0)
+
+// Programmatic dependent launch (sm_90+): a kernel launched with the attribute may be scheduled while its predecessor on the
+// stream is still running; it must execute pdl_wait() before touching anything the predecessor produces (or consumes) --
+// every kernel launched through launch_pdl() does so as its first statement, so only launch latency overlaps.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
+template <typename... KArgs, typename... Args>
+static inline cudaError_t launch_pdl(bool pdl, void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = pdl ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kern, KArgs(args)...);
+}
 
 // ---- gemm_nt.cu
 struct GemmArgs {

@@ -43,6 +43,8 @@ gemm_nt_kernel(GemmArgs g, int tiles_m, int tiles_n, int c_vec) {
     constexpr int WARPS_N = BN / WN;
     constexpr int MI = WM / 8, NI = WN / 8;
     extern __shared__ __align__(16) double smem[];
+    pdl_wait();
+    pdl_launch_dependents();
     double* As = smem;
     double* Bs = smem + (size_t)STAGES * BM * PITCH;
 
@@ -227,7 +229,7 @@ static int launch_cfg(Ctx* ctx, const GemmArgs& g, cudaStream_t st) {
         BGP_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM));
         attr_done[aligned] |= dev_bit;
     }
-    kern<<<tiles_m * tiles_n, NT, SMEM, st>>>(g, tiles_m, tiles_n, c_vec);
+    BGP_CUDA_OK(launch_pdl(ctx->pdl && ctx->pdl_chain, kern, dim3(tiles_m * tiles_n), dim3(NT), SMEM, st, g, tiles_m, tiles_n, c_vec));
     BGP_LAUNCH_OK(ctx);
     return 0;
 }

@@ -127,6 +127,8 @@ leaf_potrf_trtri_kernel(double* A, int64_t lda, int n, double* dinv, int32_t* in
     __shared__ double colbuf[64];
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int fr = lane >> 2, fk = lane & 3;
+    pdl_wait();
+    pdl_launch_dependents();
     long long t_prev = clock64();
 
     {
@@ -267,7 +269,8 @@ static int launch_leaf(Ctx* ctx, double* A, int64_t lda, int n, double* dinv, in
         BGP_CUDA_OK(cudaFuncSetAttribute(leaf_potrf_trtri_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
         attr_done |= bit;
     }
-    leaf_potrf_trtri_kernel<<<1, 256, SMEM, st>>>(A, lda, n, dinv, ctx->d_info, gofs, ctx->d_scal);
+    BGP_CUDA_OK(launch_pdl(ctx->pdl && ctx->pdl_chain, leaf_potrf_trtri_kernel, dim3(1), dim3(256), SMEM, st, A, lda, n, dinv, ctx->d_info, gofs,
+                           ctx->d_scal));
     BGP_LAUNCH_OK(ctx);
     return 0;
 }

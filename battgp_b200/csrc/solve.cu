@@ -30,14 +30,12 @@ __global__ void __launch_bounds__(256) trsv_first_kernel(const double* __restric
     }
 }
 
-// forward step for block k (rows k0..k0+nbk-1 solved, x holds x_k at x[k0..]):
-//   rows i >= k0+nbk:  b[i] -= L[i, k0:k0+nbk] . x_k ;  CTA 0 then x[k0+nbk ..] = Dinv_{k+1} * b[k0+nbk ..]
-// Each warp owns 16 rows and issues all 64 loads of its 16x128 slab before reducing (the sweep is pure latency).
-__device__ __forceinline__ void rows16_dot(const double* __restrict__ base, int64_t ld, int nrows, int ncols, int lane,
-                                           double x0, double x1, double x2, double x3, double (&out)[16]) {
-    double a[16][4];
+// RW rows per warp, 128 columns: issue all loads of the RW x 128 slab (4 per lane and row) before anything is reduced
+template <int RW>
+__device__ __forceinline__ void rows_load(const double* __restrict__ base, int64_t ld, int nrows, int ncols, int lane,
+                                          double (&a)[RW][4]) {
 #pragma unroll
-    for (int u = 0; u < 16; u++) {
+    for (int u = 0; u < RW; u++) {
         const double* lp = base + (int64_t)u * ld;
         const bool rok = u < nrows;
         a[u][0] = (rok && lane < ncols) ? lp[lane] : 0.0;
@@ -45,47 +43,65 @@ __device__ __forceinline__ void rows16_dot(const double* __restrict__ base, int6
         a[u][2] = (rok && lane + 64 < ncols) ? lp[lane + 64] : 0.0;
         a[u][3] = (rok && lane + 96 < ncols) ? lp[lane + 96] : 0.0;
     }
-#pragma unroll
-    for (int u = 0; u < 16; u++) out[u] = warp_sum(a[u][0] * x0 + a[u][1] * x1 + a[u][2] * x2 + a[u][3] * x3);
 }
+// lane u < RW returns the dot product of row u with x (x0..x3 = this lane's four entries of x)
+template <int RW>
+__device__ __forceinline__ double rows_reduce(const double (&a)[RW][4], double x0, double x1, double x2, double x3, int lane) {
+    double mine = 0.0;
+#pragma unroll
+    for (int u = 0; u < RW; u++) {
+        const double s = warp_sum(a[u][0] * x0 + a[u][1] * x1 + a[u][2] * x2 + a[u][3] * x3);
+        if (lane == u) mine = s;
+    }
+    return mine;
+}
+__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 
-__global__ void __launch_bounds__(256)
+// The sweeps are chains of ~N/128 dependent launches.  Steps after the first of a sweep are launched with programmatic
+// dependent launch (common.cuh): a step's CTAs become resident while earlier steps still run, pull their slab of L into
+// registers (L is not written during a sweep) and the next diagonal-block inverse towards L2, and only then wait for the
+// predecessor -- launch latency and the DRAM latency of the slab leave the dependent chain.
+//
+// forward step for block k (rows k0..k0+nbk-1 solved, x holds x_k at x[k0..]):
+//   rows i >= k0+nbk:  b[i] -= L[i, k0:k0+nbk] . x_k ;  CTA 0 then x[k0+nbk ..] = Dinv_{k+1} * b[k0+nbk ..]
+// 16 warps x 8 rows = 128 rows per CTA.
+constexpr int TRSV_RW = 8;
+__global__ void __launch_bounds__(512)
 trsv_fwd_step_kernel(const double* __restrict__ L, int64_t ldl, int64_t n, int64_t k0, int nbk,
                      const double* __restrict__ dinv_next, double* b, double* x) {
     __shared__ double sx[LEAF];
     __shared__ double sb[LEAF];
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int64_t r0 = k0 + nbk + (int64_t)blockIdx.x * LEAF;
+    const int64_t wr0 = r0 + warp * TRSV_RW;
+    const int nrows = (int)max((int64_t)0, min((int64_t)TRSV_RW, n - wr0));
+    pdl_launch_dependents();
+    double a[TRSV_RW][4];
+    rows_load<TRSV_RW>(L + wr0 * ldl + k0, ldl, nrows, nbk, lane, a);
+    if (blockIdx.x == 0) {
+        const char* dp = reinterpret_cast<const char*>(dinv_next);
+        for (int i = tid; i < LEAF * LEAF * 8 / 128; i += 512) prefetch_l2(dp + (size_t)i * 128);
+    }
+    pdl_wait();
     if (tid < LEAF) sx[tid] = tid < nbk ? x[k0 + tid] : 0.0;
     __syncthreads();
-    const int64_t r0 = k0 + nbk + (int64_t)blockIdx.x * LEAF;
-    const int64_t wr0 = r0 + warp * 16;
-    const int nrows = (int)max((int64_t)0, min((int64_t)16, n - wr0));
-    double s[16];
-    rows16_dot(L + wr0 * ldl + k0, ldl, nrows, nbk, lane, sx[lane], sx[lane + 32], sx[lane + 64], sx[lane + 96], s);
-    // lane u finishes row u of this warp
-    double mine = 0.0;
-#pragma unroll
-    for (int u = 0; u < 16; u++) if (lane == u) mine = s[u];
+    const double mine = rows_reduce<TRSV_RW>(a, sx[lane], sx[lane + 32], sx[lane + 64], sx[lane + 96], lane);
     if (lane < nrows) {
         const double nb_ = b[wr0 + lane] - mine;
         b[wr0 + lane] = nb_;
-        if (blockIdx.x == 0) sb[warp * 16 + lane] = nb_;
+        if (blockIdx.x == 0) sb[warp * TRSV_RW + lane] = nb_;
     }
     if (blockIdx.x != 0) return;
     __syncthreads();
+    // x_{k+1} = Dinv_{k+1} * b_{k+1}: again 8 rows per warp
     const int nnext = (int)min((int64_t)LEAF, n - r0);
-    if (lane >= 0) {     // x_{k+1} = Dinv_{k+1} * b_{k+1}: again 16 rows per warp
-        const int rr0 = warp * 16;
-        const int nr = max(0, min(16, nnext - rr0));
-        double t[16];
-        rows16_dot(dinv_next + rr0 * LEAF, LEAF, nr, nnext, lane, lane < nnext ? sb[lane] : 0.0,
-                   lane + 32 < nnext ? sb[lane + 32] : 0.0, lane + 64 < nnext ? sb[lane + 64] : 0.0,
-                   lane + 96 < nnext ? sb[lane + 96] : 0.0, t);
-        double m2 = 0.0;
-#pragma unroll
-        for (int u = 0; u < 16; u++) if (lane == u) m2 = t[u];
-        if (lane < nr) x[r0 + rr0 + lane] = m2;
-    }
+    const int rr0 = warp * TRSV_RW;
+    const int nr = max(0, min(TRSV_RW, nnext - rr0));
+    double t[TRSV_RW][4];
+    rows_load<TRSV_RW>(dinv_next + rr0 * LEAF, LEAF, nr, nnext, lane, t);
+    const double m2 = rows_reduce<TRSV_RW>(t, lane < nnext ? sb[lane] : 0.0, lane + 32 < nnext ? sb[lane + 32] : 0.0,
+                                           lane + 64 < nnext ? sb[lane + 64] : 0.0, lane + 96 < nnext ? sb[lane + 96] : 0.0, lane);
+    if (lane < nr) x[r0 + rr0 + lane] = m2;
 }
 
 // x[k0 + i] = sum_r Dinv[r][i] * b[k0 + r]   (last block of the backward sweep = first to be solved)
@@ -112,15 +128,23 @@ trsv_bwd_step_kernel(const double* __restrict__ L, int64_t ldl, int64_t k0, int 
     __shared__ double part[4][LEAF];
     __shared__ double sb[LEAF];
     const int tid = threadIdx.x;
-    if (tid < LEAF) sx[tid] = tid < nbk ? x[k0 + tid] : 0.0;
-    __syncthreads();
     const int cl = tid & (LEAF - 1), q = tid >> 7;
     const int64_t c = k0 - LEAF - (int64_t)blockIdx.x * LEAF + cl;   // CTA 0: columns k0-128 .. k0-1 (always >= 0)
+    pdl_launch_dependents();
+    double v[32];
     {
         const double* lp = L + (k0 + q * 32) * ldl + c;
-        double v[32];
 #pragma unroll
         for (int r = 0; r < 32; r++) v[r] = (q * 32 + r < nbk) ? lp[(int64_t)r * ldl] : 0.0;
+    }
+    if (blockIdx.x == 0) {
+        const char* dp = reinterpret_cast<const char*>(dinv_prev);
+        for (int i = tid; i < LEAF * LEAF * 8 / 128; i += 512) prefetch_l2(dp + (size_t)i * 128);
+    }
+    pdl_wait();
+    if (tid < LEAF) sx[tid] = tid < nbk ? x[k0 + tid] : 0.0;
+    __syncthreads();
+    {
         double s0 = 0.0, s1 = 0.0;
 #pragma unroll
         for (int r = 0; r < 32; r += 2) { s0 = fma(v[r], sx[q * 32 + r], s0); s1 = fma(v[r + 1], sx[q * 32 + r + 1], s1); }
@@ -160,7 +184,9 @@ int trsv_lower(Ctx* ctx, const double* L, int64_t n, int64_t ldl, const double* 
         const int64_t k0 = k * LEAF;
         const int64_t rows = n - k0 - LEAF;
         const unsigned grid = (unsigned)((rows + LEAF - 1) / LEAF);
-        trsv_fwd_step_kernel<<<grid, 256, 0, st>>>(L, ldl, n, k0, LEAF, dinv + (k + 1) * (int64_t)LEAF * LEAF, b, x);
+        // the first step of the sweep is serialised normally: whatever produced L must be complete before a slab is read
+        BGP_CUDA_OK(launch_pdl(ctx->pdl != 0 && k > 0, trsv_fwd_step_kernel, dim3(grid), dim3(512), 0, st, L, ldl, n, k0, (int)LEAF,
+                               dinv + (k + 1) * (int64_t)LEAF * LEAF, b, x));
         BGP_LAUNCH_OK(ctx);
     }
     return 0;
@@ -178,7 +204,8 @@ int trsv_lower_t(Ctx* ctx, const double* L, int64_t n, int64_t ldl, const double
         const int64_t k0 = k * LEAF;
         const int nbk = (int)min((int64_t)LEAF, n - k0);
         const unsigned grid = (unsigned)(k0 / LEAF);
-        trsv_bwd_step_kernel<<<grid, 512, 0, st>>>(L, ldl, k0, nbk, dinv + (k - 1) * (int64_t)LEAF * LEAF, b, x);
+        BGP_CUDA_OK(launch_pdl(ctx->pdl != 0 && k < nblk - 1, trsv_bwd_step_kernel, dim3(grid), dim3(512), 0, st, L, ldl, k0, nbk,
+                               dinv + (k - 1) * (int64_t)LEAF * LEAF, b, x));
         BGP_LAUNCH_OK(ctx);
     }
     return 0;

@@ -73,7 +73,7 @@ void bgp_ctx_destroy(bgp_ctx* ctx);
  * be factorised -- 512 below "sched_t1024" rows, 1024 from there, 2048 from "sched_t2048" and 4096 from "sched_t4096" on the
  * int8 path, "sched_w0"/"sched_w1" cap the first two panels), "lookahead" 0/1, "ozaki" 0/1 (trailing updates on the int8
  * tcgen05 path, fp64-accurate), "oz_tpc"/"oz_cluster" (tiles per CTA / cluster size of that kernel), "gemm_cfg" (probing),
- * "trace" 0/1 (bgp_potrf prints a per-panel event timeline to stderr; diagnostics). returns 0 or BGP_E_ARG */
+ * "pdl" 0/1 (programmatic dependent launch of the dependent-kernel chains: triangular sweeps, leaf + small GEMMs), "trace" 0/1 (bgp_potrf prints a per-panel event timeline to stderr; diagnostics). returns 0 or BGP_E_ARG */
 int  bgp_ctx_set(bgp_ctx* ctx, const char* key, int value);
 /* Optional scratch for bgp_potrf's int8/tcgen05 trailing updates ("ozaki" knob, csrc/ozaki.cu): the caller (torch)
  * owns the memory; bgp_potrf uses the path only when at least bgp_potrf_workspace_bytes(ctx, n) bytes are set. */

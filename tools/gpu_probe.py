@@ -341,3 +341,27 @@ if "trace" in what:
             eng.set("trace", 0)
             print(json.dumps({"op": "potrf_trace_total", "n": n, "trace": tr, "ms": e0.elapsed_time(e1)}), flush=True)
         del K
+if "pdl" in what:
+    # programmatic dependent launch on the chain kernels (leaf + DMMA GEMMs): on/off
+    spec = E.battgp_spec()
+    for n in (1024, 2048, 4096, 8192, 16384, 40000):
+        x, y = synth_field_data(n, 0)
+        xd = torch.tensor(x, device=dev)
+        K = E.alloc_matrix(n, n, dev)
+        eng.set("ozaki", 1)
+        for pdl in (0, 1, 0, 1):
+            eng.set("pdl", pdl)
+            best = 1e30
+            for r in range(4 if n < 20000 else 2):
+                eng.cov_build(spec, xd, noise=2.33e-6, symmetric=True, out=K)
+                torch.cuda.synchronize()
+                e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+                e0.record(); info, ld, dinv = eng.potrf(K); e1.record(); torch.cuda.synchronize()
+                best = min(best, e0.elapsed_time(e1))
+            yd = torch.tensor(y, device=dev)
+            z, al = eng.potrs_vec(K, dinv, yd)
+            bs = ev(lambda: eng.potrs_vec(K, dinv, yd), reps=5)
+            print(json.dumps({"op": "potrf_pdl", "n": n, "pdl": pdl, "info": info, "logdet": ld, "ms": round(best, 4),
+                              "potrs_vec_ms": round(bs, 4), "alpha_sum": float(al.sum()), "z_sq": float(z @ z)}), flush=True)
+        eng.set("pdl", 1)
+        del K
