@@ -28,6 +28,8 @@ int64_t oz_slice_buffer_bytes(int64_t rows, int64_t K);
 int oz_slice(Ctx*, const double*, int64_t, int64_t, int64_t, void*, cudaStream_t, const int32_t* blkmap = nullptr, int64_t blkrows = 0);
 int oz_gemm(Ctx*, const void*, int64_t, int64_t, const void*, int64_t, int64_t, int64_t, int64_t, int64_t, double, double*,
             int64_t, int, int64_t, int64_t, cudaStream_t, int tiles_per_cta = 0);
+int oz2_residues(Ctx*, const double*, int64_t, int64_t, int64_t, int8_t*, int32_t*, cudaStream_t);
+int oz2_crt(Ctx*, const int32_t*, int64_t, int64_t, const int32_t*, const int32_t*, double, double*, int64_t, cudaStream_t);
 int potri(Ctx*, double*, int64_t, int64_t, const double*, double*, int64_t, cudaStream_t);
 int lml_grad(Ctx*, const bgp_kernel_spec*, const double*, int64_t, int64_t, const double*, int64_t, const double*,
              double*, cudaStream_t);
@@ -515,6 +517,19 @@ int bgp_gemm_nt_i8(bgp_ctx* c, int64_t M, int64_t N, int64_t K, double alpha, co
     const bool same = (A == B && lda == ldb && M == N);
     if (!same && (rc = oz_slice(ctx, B, N, K, ldb, wb, st))) return rc;
     return oz_gemm(ctx, wa, M, 0, same ? wa : wb, N, 0, M, N, K, alpha, C, ldc, tri ? 1 : 0, roff, coff, st);
+}
+
+int bgp_oz2_residues(bgp_ctx* c, const double* A, int64_t rows, int64_t K, int64_t ld, int8_t* residues, int32_t* expo, void* stream) {
+    CTX_OR_FAIL(c);
+    if (rows < 0 || K < 0 || (rows > 0 && K > 0 && (!A || !residues || !expo || ld < K))) return BGP_E_ARG;
+    return oz2_residues(ctx, A, rows, K, ld, residues, expo, (cudaStream_t)stream);
+}
+
+int bgp_oz2_crt(bgp_ctx* c, const int32_t* G, int64_t M, int64_t N, const int32_t* ea, const int32_t* eb, double alpha, double* C,
+                int64_t ldc, void* stream) {
+    CTX_OR_FAIL(c);
+    if (M < 0 || N < 0 || (M > 0 && N > 0 && (!G || !ea || !eb || !C || ldc < N))) return BGP_E_ARG;
+    return oz2_crt(ctx, G, M, N, ea, eb, alpha, C, ldc, (cudaStream_t)stream);
 }
 
 int bgp_potri(bgp_ctx* c, double* L, int64_t n, int64_t ldl, const double* dinv, double* work, int64_t ldw,

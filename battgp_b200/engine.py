@@ -265,6 +265,27 @@ class Engine:
         _lib.check(rc, "bgp_oz_gemm")
         return C_
 
+    # components of the modular (CRT) int8 emulation (csrc/ozaki2.cu; groundwork, not used by potrf yet)
+    def oz2_residues(self, A: torch.Tensor):
+        """A [rows, K] fp64 -> (residues [16, rows, K] int8, exponents [rows] int32)."""
+        _check_f64_cuda(A, "A", self.device)
+        rows, K = A.shape
+        res = torch.empty((16, rows, K), dtype=torch.int8, device=self.device)
+        expo = torch.empty(rows, dtype=torch.int32, device=self.device)
+        rc = self.L.bgp_oz2_residues(self.h, _ptr(A), rows, K, self._ld(A), _ptr(res), _ptr(expo), self._stream())
+        _lib.check(rc, "bgp_oz2_residues")
+        return res, expo
+
+    def oz2_crt(self, G: torch.Tensor, ea: torch.Tensor, eb: torch.Tensor, C_: torch.Tensor, alpha: float = 1.0):
+        """G [16, M, N] int32 (contiguous) -> C += alpha * 2^(ea_i + eb_j - 110) * CRT(G)."""
+        _check_f64_cuda(C_, "C", self.device)
+        if G.dtype != torch.int32 or not G.is_contiguous() or G.shape[0] != 16 or tuple(G.shape[1:]) != tuple(C_.shape):
+            raise ValueError("oz2_crt: G must be a contiguous int32 [16, M, N] tensor matching C")
+        M, N = C_.shape
+        rc = self.L.bgp_oz2_crt(self.h, _ptr(G), M, N, _ptr(ea), _ptr(eb), float(alpha), _ptr(C_), self._ld(C_), self._stream())
+        _lib.check(rc, "bgp_oz2_crt")
+        return C_
+
     # ------------------------------------------------------------------ K4
     def potrf(self, A: torch.Tensor):
         """In-place lower Cholesky.  ``A`` is n x n, or (n + mx) x n with mx extra right-hand-side rows that leave as

@@ -128,6 +128,16 @@ int bgp_oz_gemm(bgp_ctx* ctx, const void* bufA, int64_t rowsA, int64_t arow0, co
                 int64_t M, int64_t N, int64_t K, double alpha, double* C, int64_t ldc, int tri, int64_t roff, int64_t coff,
                 void* stream);
 
+/* Components of the modular (Chinese-remainder) int8 emulation -- 16 products instead of 36 (csrc/ozaki2.cu, DESIGN.md section 5;
+ * design groundwork: the tensor-core kernel between them is next, bgp_potrf does not use them yet).
+ * bgp_oz2_residues: A [rows, K] fp64 (ld) -> residues [16][rows][K] int8 (symmetric residues of trunc(a 2^(55-e_row)) for the
+ *   moduli 256,255,253,251,247,241,239,233,229,227,223,217,211,199,197,193) and expo [rows] (2^e >= 2 max|row|; INT_MIN for a
+ *   row holding NaN/Inf).
+ * bgp_oz2_crt: G [16][M][N] int32 (G_j = A_j B_j^T) -> C[i][j] += alpha * 2^(ea_i + eb_j - 110) * C'_ij, C' reconstructed exactly. */
+int bgp_oz2_residues(bgp_ctx* ctx, const double* A, int64_t rows, int64_t K, int64_t ld, int8_t* residues, int32_t* expo, void* stream);
+int bgp_oz2_crt(bgp_ctx* ctx, const int32_t* G, int64_t M, int64_t N, const int32_t* ea, const int32_t* eb, double alpha, double* C,
+                int64_t ldc, void* stream);
+
 /* ---- K4: Cholesky -------------------------------------------------------------------------------------
  * replaces torch.linalg.cholesky_ex inside GPyTorch's psd_safe_cholesky, reached from ExactGP.__call__
  * (battcellgp_full.py:173, standard_models.py:41) and ExactMarginalLogLikelihood (training.py:40).
