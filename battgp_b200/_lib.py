@@ -55,6 +55,7 @@ SIGNATURES = {
     "bgp_oz_slice": (C.c_int, [_P, _P, _I64, _I64, _I64, _P, _I64, _P]),
     "bgp_oz_slice_gather": (C.c_int, [_P, _P, _I64, _I64, _I64, _P, _I64, _P, _I64, _P]),
     "bgp_oz_gemm": (C.c_int, [_P, _P, _I64, _I64, _P, _I64, _I64, _I64, _I64, _I64, _D, _P, _I64, C.c_int, _I64, _I64, _P]),
+    "bgp_panel_schedule": (C.c_int, [_I64, _I64, C.c_int, C.c_int, C.POINTER(_I64), C.c_int]),
     "bgp_oz2_residues": (C.c_int, [_P, _P, _I64, _I64, _I64, _P, _P, _P]),
     "bgp_oz2_crt": (C.c_int, [_P, _P, _I64, _I64, _P, _P, _D, _P, _I64, _P]),
     "bgp_gemm_nt_i8_work_bytes": (_I64, [_I64, _I64, _I64]),

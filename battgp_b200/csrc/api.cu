@@ -307,6 +307,18 @@ int bgp_ctx_set(bgp_ctx* p, const char* key, int value) {
     return BGP_E_ARG;
 }
 
+int bgp_panel_schedule(int64_t rows, int64_t n, int ozaki, int nb, int64_t* starts, int cap) {
+    if (rows < n || n < 0 || nb < 0 || (nb > 0 && nb % LEAF != 0) || cap < 0 || (cap > 0 && !starts)) return BGP_E_ARG;
+    Ctx c;                       // defaults of a fresh context; no CUDA call is made
+    c.ozaki = ozaki ? 1 : 0;
+    c.nb = nb;
+    PanelSchedule S;
+    make_schedule(&c, rows, n, S);
+    const int np = (int)S.npanels();
+    for (int i = 0; i <= np && i < cap; i++) starts[i] = S.start[i];
+    return np;
+}
+
 int64_t bgp_potrf_workspace_bytes(const bgp_ctx* p, int64_t n) {
     if (!p || n <= 0) return 0;
     const Ctx* c = reinterpret_cast<const Ctx*>(p);

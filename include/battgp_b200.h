@@ -78,6 +78,9 @@ int  bgp_ctx_set(bgp_ctx* ctx, const char* key, int value);
 /* Optional scratch for bgp_potrf's int8/tcgen05 trailing updates ("ozaki" knob, csrc/ozaki.cu): the caller (torch)
  * owns the memory; bgp_potrf uses the path only when at least bgp_potrf_workspace_bytes(ctx, n) bytes are set. */
 int64_t bgp_potrf_workspace_bytes(const bgp_ctx* ctx, int64_t n);
+/* host-only introspection (no CUDA call): the panel boundaries bgp_potrf_aug uses for a [rows, n] factorisation with the
+ * default schedule knobs ("ozaki" 0/1, "nb" 0 = automatic).  Writes min(npanels + 1, cap) column offsets, returns npanels. */
+int  bgp_panel_schedule(int64_t rows, int64_t n, int ozaki, int nb, int64_t* starts, int cap);
 int  bgp_ctx_set_workspace(bgp_ctx* ctx, void* ptr, int64_t bytes);
 /* counts kernels launched through this context since creation (bench.py's gpu_launches) */
 int64_t bgp_ctx_launches(const bgp_ctx* ctx);

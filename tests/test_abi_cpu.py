@@ -80,3 +80,31 @@ def test_product_code_never_imports_the_oracle():
             if f.endswith(".py"):
                 src = open(os.path.join(dirpath, f)).read()
                 assert not re.search(r"^\s*(from|import)\s+oracle\b", src, flags=re.M), f
+
+
+def _schedule(rows, n, ozaki=1, nb=0):
+    L = _lib.lib()
+    buf = (C.c_int64 * 4096)()
+    np_ = L.bgp_panel_schedule(rows, n, ozaki, nb, buf, 4096)
+    assert np_ >= 0
+    return [int(buf[i]) for i in range(np_ + 1)]
+
+
+def test_panel_schedule_covers_the_columns_and_narrows_towards_the_end():
+    """Host logic of the look-ahead Cholesky (api.cu make_schedule; no CUDA call): panels tile [0, n) exactly, every panel but
+    the last is a multiple of 128 wide, widths follow the remaining rows (2048 / 1024 / 512 on the int8 path, never above 1024
+    on the DMMA-only path) and never grow again, and the "nb" knob gives uniform panels."""
+    for rows, n in ((40300, 40000), (40000, 40000), (16384, 16384), (8192, 8192), (3300, 3000), (1000, 1000), (129, 129), (5, 5)):
+        for oz in (0, 1):
+            s = _schedule(rows, n, oz)
+            assert s[0] == 0 and s[-1] == n and all(b > a for a, b in zip(s, s[1:]))
+            w = [b - a for a, b in zip(s, s[1:])]
+            assert all(x % 128 == 0 for x in w[:-1])
+            assert all(w[i + 1] <= w[i] for i in range(len(w) - 1))
+            assert max(w) <= (2048 if oz else 1024)
+    w = [b - a for a, b in zip(*(lambda s: (s, s[1:]))(_schedule(40300, 40000, 1)))]
+    assert w[0] == 2048 and 1024 in w and w[-2] == 512
+    assert _schedule(8192, 8192, 1) == list(range(0, 8193, 512))
+    s = _schedule(5000, 5000, 1, nb=1024)
+    assert s == [0, 1024, 2048, 3072, 4096, 5000]
+    assert _schedule(0, 0) == [0]
