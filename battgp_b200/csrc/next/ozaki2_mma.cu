@@ -1,0 +1,361 @@
+// DRAFT -- NOT BUILT INTO libbattgp_b200.so (battgp_b200/build.py SOURCES does not list it) and never run on a GPU yet.
+// Compile check only:  nvcc -gencode arch=compute_100a,code=sm_100a -std=c++17 -I.. -c next/ozaki2_mma.cu
+//
+// First (correctness-first, no multicast) form of the tensor-core kernel of the MODULAR int8 emulation (DESIGN.md section 5,
+// tools/ozaki2_model.py, csrc/ozaki2.cu): C'_j = A_j B_j^T for the 16 moduli, two moduli per TMEM pass, residues of the
+// accumulators parked as one byte per element and modulus for the reconstruction kernel.
+//
+//   operand image  : like ozaki.cu's digit planes but 16 residue planes -- [k-block][128-row block][plane] tiles of
+//                    128 rows x 64 B in the 64-byte-swizzled K-major layout the UMMA descriptors expect
+//                    (oz2_slice_swz_kernel); per-row exponents (int32) behind the planes
+//   tile           : 128 x 256 per CTA, tcgen05.mma cta_group::1 kind::i8 with N = 256; accumulator of plane 2p at TMEM
+//                    columns [0,256), of plane 2p+1 at [256,512); 8 passes per tile, each a full K loop
+//   stage          : A 2 planes x 8 KB + B 2 planes x 2 row blocks x 8 KB = 48 KB, 4 stages
+//   pass epilogue  : tcgen05.ld, t = acc mod p in [0,p), 32 bytes per thread and plane chunk -> T[plane][row][col] (uint8)
+//   reconstruction : oz2_crt_u8_kernel -- the arithmetic of oz2_crt_kernel (validated bit for bit against the model),
+//                    fed from T instead of int32 accumulators
+// Next steps once this form is parity-green: (1) 2x2 cluster with operand multicast (fill per modulus and k-step 24 -> 12 KB;
+// without it the kernel moves as many bytes as ozaki.cu and stays L2-bound), (2) persistent tile loop with the TMEM drain
+// overlapped as in oz_mma_persistent_kernel, (3) fuse the reconstruction into the last pass.
+#include <climits>
+#include "../common.cuh"
+
+namespace bgp {
+namespace oz2draft {
+
+constexpr int NMOD = 16, BETA = 55;
+constexpr int BM = 128, BN = 256, BK = 64, STAGES = 4, PASSES = NMOD / 2;
+constexpr int TILE = 128 * BK;                         // one plane of a 128-row block for one k-block: 8192 B
+constexpr int A_STAGE = 2 * TILE;                      // 16 KB
+constexpr int B_STAGE = 2 * 2 * TILE;                  // 32 KB: [plane][256 rows]
+__host__ __device__ constexpr int modulus(int j) {
+    constexpr int m[NMOD] = {256, 255, 253, 251, 247, 241, 239, 233, 229, 227, 223, 217, 211, 199, 197, 193};
+    return m[j];
+}
+
+// ---------------------------------------------------------------------------------------------------- PTX helpers (as in ozaki.cu)
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                 : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+    return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {      // bounded: a wrong descriptor traps, never hangs
+    for (uint32_t it = 0; it < (1u << 24); ++it)
+        if (mbar_try_wait(bar, parity)) return;
+    __trap();
+}
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+__device__ __forceinline__ uint64_t desc_sw64(uint32_t saddr) {     // K-major, SWIZZLE_64B, SBO = 512 B, version 1
+    uint64_t d = 0;
+    d |= (uint64_t)((saddr >> 4) & 0x3FFF);
+    d |= (uint64_t)((512 >> 4) & 0x3FFF) << 32;
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)4 << 61;
+    return d;
+}
+__device__ __forceinline__ void mma_i8(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t accumulate) {
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+                 "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, p;\n\t}"
+                 ::"r"(tmem_d), "l"(da), "l"(db), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void commit(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+                 "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+                 : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+                   "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
+                   "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
+                   "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+                 : "r"(taddr) : "memory");
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile("{\n\t.reg .b32 rx;\n\t.reg .pred px;\n\telect.sync rx|px, 0xffffffff;\n\tselp.u32 %0, 1, 0, px;\n\t}" : "=r"(pred)::"memory");
+    return pred != 0;
+}
+
+// ---------------------------------------------------------------------------------------------------- residues, swizzled image
+__device__ __forceinline__ int swz64(int r8, int kb64) {        // Swizzle<2,4,3> inside an 8-row x 64-byte atom
+    const int chunk = (kb64 >> 4) ^ ((r8 >> 1) & 3);
+    return r8 * 64 + chunk * 16 + (kb64 & 15);
+}
+
+template <int J>
+__device__ __forceinline__ void residues16(uint32_t c0, uint32_t c1, uint32_t c2, bool neg, int8_t (&out)[NMOD]) {
+    if constexpr (J < NMOD) {
+        constexpr uint32_t p = (uint32_t)modulus(J);
+        constexpr uint32_t m20 = (uint32_t)((1ull << 20) % p), m40 = (uint32_t)((1ull << 40) % p);
+        uint32_t r = (c0 + c1 * m20 + c2 * m40) % p;
+        if (neg && r) r = p - r;
+        out[J] = (int8_t)((r >= (p + 1) / 2) ? (int)r - (int)p : (int)r);
+        residues16<J + 1>(c0, c1, c2, neg, out);
+    }
+}
+
+// grid.x = rows_pad / 8, block = 512 = 8 rows x 64 chunk-threads; thread (row, c) handles 16 consecutive k (one 16-byte chunk
+// of every plane), like oz_slice_kernel.  Image bytes: rows_pad * K * 16, exponents (int32) kept separately.
+__global__ void __launch_bounds__(512)
+slice_swz_kernel(const double* __restrict__ P, int64_t rows, int64_t K, int64_t ld, int8_t* __restrict__ out,
+                 int32_t* __restrict__ expo, int64_t nrb) {
+    __shared__ unsigned long long smax[8];
+    const int tid = threadIdx.x, r8 = tid >> 6, ct = tid & 63;
+    const int64_t row = (int64_t)blockIdx.x * 8 + r8;
+    if (ct == 0) smax[r8] = 0ull;
+    __syncthreads();
+    const int64_t nchunks = K / 16;
+    const bool live = row < rows;
+    unsigned long long mb = 0ull;
+    if (live)
+        for (int64_t c = ct; c < nchunks; c += 64)
+            for (int i = 0; i < 16; i++) {
+                const unsigned long long b = (unsigned long long)__double_as_longlong(P[row * ld + c * 16 + i]) & 0x7FFFFFFFFFFFFFFFull;
+                mb = b > mb ? b : mb;
+            }
+    atomicMax(&smax[r8], mb);
+    __syncthreads();
+    const unsigned long long bits = smax[r8];
+    const bool bad = (bits >> 52) == 0x7FFull;
+    int e = 0;
+    if (!bad && bits != 0) { int fe; (void)frexp(__longlong_as_double((long long)bits), &fe); e = fe + 1; }
+    if (ct == 0 && row < nrb * 128) expo[row] = bad ? INT_MIN : e;
+    const int64_t rb = row >> 7;
+    const int rin = (int)(row & 127);
+    for (int64_t c = ct; c < nchunks; c += 64) {
+        uint32_t w[NMOD][4];
+#pragma unroll
+        for (int j = 0; j < NMOD; j++) w[j][0] = w[j][1] = w[j][2] = w[j][3] = 0u;
+        if (live && !bad) {
+#pragma unroll
+            for (int i = 0; i < 16; i++) {
+                const long long v = __double2ll_rz(scalbn(P[row * ld + c * 16 + i], BETA - e));
+                const bool neg = v < 0;
+                const unsigned long long u = (unsigned long long)(neg ? -v : v);
+                int8_t r[NMOD];
+                residues16<0>((uint32_t)(u & 0xFFFFFu), (uint32_t)((u >> 20) & 0xFFFFFu), (uint32_t)(u >> 40), neg, r);
+#pragma unroll
+                for (int j = 0; j < NMOD; j++) w[j][i >> 2] |= ((uint32_t)(uint8_t)r[j]) << ((i & 3) * 8);
+            }
+        }
+        const int64_t kb = (c * 16) >> 6;
+        const int kin = (int)((c * 16) & 63);
+        int8_t* base = out + ((kb * nrb + rb) * NMOD) * (int64_t)TILE + (rin >> 3) * 512 + swz64(rin & 7, kin);
+#pragma unroll
+        for (int j = 0; j < NMOD; j++)
+            *reinterpret_cast<uint4*>(base + (int64_t)j * TILE) = make_uint4(w[j][0], w[j][1], w[j][2], w[j][3]);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------- MMA kernel
+struct Args {
+    const int8_t* sa; int64_t nrb_a; int64_t arow0;      // residue planes of A, 128-row blocks in its buffer, first row (multiple of 128)
+    const int8_t* sb; int64_t nrb_b; int64_t brow0;      // residue planes of B, first row (multiple of 256 for now)
+    uint8_t* T; int64_t tm, tn;                          // T[NMOD][tm][tn] bytes, tm >= tiles_m * 128, tn >= tiles_n * 256
+    int M, N, K;
+    int tri; int64_t roff, coff;
+};
+
+template <int J>
+__device__ __forceinline__ uint32_t mod_plane(int plane, int v) {       // v mod p_plane in [0, p), plane known at run time
+    if constexpr (J < NMOD) {
+        if (plane == J) { constexpr int p = modulus(J); int t = v % p; return (uint32_t)(t + ((t < 0) ? p : 0)); }
+        return mod_plane<J + 1>(plane, v);
+    } else {
+        return 0u;
+    }
+}
+
+// one 128 x 256 tile per CTA, 192 threads: warp 0 producer, warp 1 MMA issuer, warps 2-5 pass epilogue.
+// Launch: grid = tiles_m * tiles_n, dynamic smem = STAGES * (A_STAGE + B_STAGE) + 1024 + 256 (opt-in attribute), then
+// crt_u8_kernel over M x ceil(N / 4) threads.
+__global__ void __launch_bounds__(192, 1) mma_kernel(Args g, int tiles_m, int tiles_n) {
+    const int tm_ = blockIdx.x % tiles_m, tn_ = blockIdx.x / tiles_m;
+    const int m0 = tm_ * BM, n0 = tn_ * BN;
+    if (g.tri && ((int64_t)n0 + g.coff > (int64_t)m0 + BM - 1 + g.roff)) return;
+
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint8_t* sA = smem;                                        // [stage][2 planes][128 x 64 B]
+    uint8_t* sB = smem + STAGES * A_STAGE;                     // [stage][2 planes][256 x 64 B]
+    uint64_t* bars = reinterpret_cast<uint64_t*>(sB + STAGES * B_STAGE);
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 2);
+    const uint32_t full0 = smem_u32(bars), empty0 = smem_u32(bars + STAGES);
+    const uint32_t tfull = smem_u32(bars + 2 * STAGES), tempty = smem_u32(bars + 2 * STAGES + 1);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (warp == 0 && lane == 0) {
+        for (int i = 0; i < STAGES; i++) { mbar_init(full0 + 8 * i, 1); mbar_init(empty0 + 8 * i, 1); }
+        mbar_init(tfull, 1);
+        mbar_init(tempty, 4);                                  // one arrival per epilogue warp
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem_base = *tmem_slot;
+    const int KB = g.K / BK;
+
+    if (warp == 0) {
+        const int64_t arb = (g.arow0 + m0) >> 7;
+        const int64_t brb = (g.brow0 + n0) >> 7;               // two consecutive 128-row blocks
+        uint32_t it = 0;
+        for (int pass = 0; pass < PASSES; pass++)
+            for (int kb = 0; kb < KB; kb++, it++) {
+                const int st = it % STAGES;
+                const uint32_t ph = (it / STAGES) & 1;
+                mbar_wait(empty0 + 8 * st, ph ^ 1);
+                if (elect_one()) {
+                    mbar_expect_tx(full0 + 8 * st, A_STAGE + B_STAGE);
+                    // planes 2*pass, 2*pass+1 of the A block are adjacent in the image: one 16 KB copy
+                    bulk_g2s(smem_u32(sA + st * A_STAGE), g.sa + (((int64_t)kb * g.nrb_a + arb) * NMOD + 2 * pass) * TILE, A_STAGE,
+                             full0 + 8 * st);
+                    // B: smem [plane][row block 0 | row block 1]; a row block past the buffer is clamped (its columns are masked later)
+#pragma unroll
+                    for (int pl = 0; pl < 2; pl++)
+#pragma unroll
+                        for (int hb = 0; hb < 2; hb++) {
+                            const int64_t b = (brb + hb < g.nrb_b) ? brb + hb : g.nrb_b - 1;
+                            bulk_g2s(smem_u32(sB + st * B_STAGE + pl * 2 * TILE + hb * TILE),
+                                     g.sb + (((int64_t)kb * g.nrb_b + b) * NMOD + 2 * pass + pl) * TILE, TILE, full0 + 8 * st);
+                        }
+                }
+                __syncwarp();
+            }
+    } else if (warp == 1) {
+        // kind::i8, D = S32, A/B = signed int8, both K-major, M = 128, N = 256
+        const uint32_t idesc = (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+        const uint64_t dzero = desc_sw64(0);
+        uint32_t it = 0;
+        for (int pass = 0; pass < PASSES; pass++) {
+            mbar_wait(tempty, (pass & 1) ^ 1);                 // the epilogue has drained the previous pass
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            for (int kb = 0; kb < KB; kb++, it++) {
+                const int st = it % STAGES;
+                const uint32_t ph = (it / STAGES) & 1;
+                mbar_wait(full0 + 8 * st, ph);
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                if (elect_one()) {
+                    const uint64_t da0 = dzero + (uint64_t)(smem_u32(sA + st * A_STAGE) >> 4);
+                    const uint64_t db0 = dzero + (uint64_t)(smem_u32(sB + st * B_STAGE) >> 4);
+#pragma unroll
+                    for (int ks = 0; ks < BK / 32; ks++)
+#pragma unroll
+                        for (int pl = 0; pl < 2; pl++)
+                            mma_i8(tmem_base + (uint32_t)pl * BN, da0 + (uint64_t)((pl * TILE + ks * 32) >> 4),
+                                   db0 + (uint64_t)((pl * 2 * TILE + ks * 32) >> 4), idesc, (kb > 0 || ks > 0) ? 1u : 0u);
+                    commit(empty0 + 8 * st);
+                    if (kb == KB - 1) commit(tfull);
+                }
+                __syncwarp();
+            }
+        }
+    } else {
+        const int q = warp & 3;                                // TMEM lane quadrant this warp may read
+        const int row = m0 + q * 32 + lane;
+        for (int pass = 0; pass < PASSES; pass++) {
+            mbar_wait(tfull, pass & 1);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+#pragma unroll 1
+            for (int pl = 0; pl < 2; pl++) {
+                const int plane = 2 * pass + pl;
+                uint8_t* trow = g.T + ((int64_t)plane * g.tm + row) * g.tn + n0;
+#pragma unroll 1
+                for (int h = 0; h < BN / 32; h++) {
+                    uint32_t v[32];
+                    tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(pl * BN + h * 32), v);
+                    uint32_t pk[8];
+#pragma unroll
+                    for (int i = 0; i < 8; i++) {
+                        pk[i] = mod_plane<0>(plane, (int)v[4 * i]) | (mod_plane<0>(plane, (int)v[4 * i + 1]) << 8) |
+                                (mod_plane<0>(plane, (int)v[4 * i + 2]) << 16) | (mod_plane<0>(plane, (int)v[4 * i + 3]) << 24);
+                    }
+                    // T is padded to whole tiles: no row/column predicate needed
+                    uint4* dst = reinterpret_cast<uint4*>(trow + h * 32);
+                    dst[0] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+                    dst[1] = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+                }
+            }
+            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+            __syncwarp();
+            if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(tempty) : "memory");
+        }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
+}
+
+// ---------------------------------------------------------------------------------------------------- reconstruction from T
+struct Consts {
+    uint32_t w[NMOD][4];
+    uint32_t p[4];
+    double wf[NMOD];
+};
+__constant__ Consts c_k;        // filled like c_oz2 in ozaki2.cu (oz2_upload_consts)
+
+// one thread per 4 consecutive columns
+__global__ void __launch_bounds__(256)
+crt_u8_kernel(const uint8_t* __restrict__ T, int64_t tm, int64_t tn, int M, int N, const int32_t* __restrict__ ea,
+              const int32_t* __restrict__ eb, double alpha, double* __restrict__ C, int64_t ldc, int tri, int64_t roff, int64_t coff) {
+    const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t nq = (N + 3) / 4;
+    if (idx >= (int64_t)M * nq) return;
+    const int64_t i = idx / nq, j0 = (idx % nq) * 4;
+    uint32_t t4[NMOD];
+#pragma unroll
+    for (int m = 0; m < NMOD; m++) t4[m] = *reinterpret_cast<const uint32_t*>(T + ((int64_t)m * tm + i) * tn + j0);
+    const int ei = ea[i];
+#pragma unroll
+    for (int c = 0; c < 4; c++) {
+        const int64_t j = j0 + c;
+        if (j >= N || (tri && j + coff > i + roff)) continue;
+        unsigned long long s[4] = {0, 0, 0, 0};
+        double est = 0.0;
+#pragma unroll
+        for (int m = 0; m < NMOD; m++) {
+            const uint32_t t = (t4[m] >> (8 * c)) & 255u;
+#pragma unroll
+            for (int k = 0; k < 4; k++) s[k] += (unsigned long long)c_k.w[m][k] * t;
+            est += (double)t * c_k.wf[m];
+        }
+        const long long q = __double2ll_rn(est);
+        long long r[4];
+#pragma unroll
+        for (int k = 0; k < 4; k++) r[k] = (long long)s[k] - q * (long long)c_k.p[k];
+#pragma unroll
+        for (int k = 0; k < 3; k++) { const long long cy = r[k] >> 32; r[k] -= cy * 4294967296ll; r[k + 1] += cy; }
+        long long hi = r[3] * 4294967296ll + r[2];
+        unsigned long long lo = ((unsigned long long)r[1] << 32) + (unsigned long long)r[0];
+        const bool neg = hi < 0;
+        if (neg) { hi = ~hi + (lo == 0 ? 1 : 0); lo = ~lo + 1ull; }
+        double mag = __ull2double_rn((unsigned long long)hi) * 18446744073709551616.0 + __ull2double_rn(lo);
+        if (neg) mag = -mag;
+        const int ej = eb[j];
+        const double val = (ei == INT_MIN || ej == INT_MIN) ? __longlong_as_double(0x7ff8000000000000ll) : scalbn(mag, ei + ej - 2 * BETA);
+        double* cp = C + i * ldc + j;
+        *cp = *cp + alpha * val;
+    }
+}
+
+// Note on p = 256: t = 0 would also be produced by a residue that is exactly 256 -- it cannot be: t is reduced to [0, p).
+// The byte therefore holds t for every modulus including 256 (t in [0, 255]).
+
+}  // namespace oz2draft
+}  // namespace bgp
