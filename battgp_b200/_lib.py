@@ -58,6 +58,8 @@ SIGNATURES = {
     "bgp_panel_schedule": (C.c_int, [_I64, _I64, C.c_int, C.c_int, C.POINTER(_I64), C.c_int]),
     "bgp_oz2_residues": (C.c_int, [_P, _P, _I64, _I64, _I64, _P, _P, _P]),
     "bgp_oz2_crt": (C.c_int, [_P, _P, _I64, _I64, _P, _P, _D, _P, _I64, _P]),
+    "bgp_oz2_gemm_work_bytes": (_I64, [_I64, _I64, _I64]),
+    "bgp_oz2_gemm": (C.c_int, [_P, _I64, _I64, _I64, _D, _P, _I64, _P, _I64, _P, _I64, _P, _I64, _P]),
     "bgp_gemm_nt_i8_work_bytes": (_I64, [_I64, _I64, _I64]),
     "bgp_gemm_nt_i8": (C.c_int, [_P, _I64, _I64, _I64, _D, _P, _I64, _P, _I64, _P, _I64, C.c_int, _I64, _I64, _P, _I64, _P]),
     "bgp_potrf_dinv_elems": (_I64, [_I64]),

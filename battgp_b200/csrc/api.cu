@@ -30,6 +30,8 @@ int oz_gemm(Ctx*, const void*, int64_t, int64_t, const void*, int64_t, int64_t, 
             int64_t, int, int64_t, int64_t, cudaStream_t, int tiles_per_cta = 0);
 int oz2_residues(Ctx*, const double*, int64_t, int64_t, int64_t, int8_t*, int32_t*, cudaStream_t);
 int oz2_crt(Ctx*, const int32_t*, int64_t, int64_t, const int32_t*, const int32_t*, double, double*, int64_t, cudaStream_t);
+int64_t oz2_gemm_work_bytes(int64_t, int64_t, int64_t);
+int oz2_gemm(Ctx*, const double*, int64_t, int64_t, const double*, int64_t, int64_t, int64_t, double, double*, int64_t, void*, cudaStream_t);
 int potri(Ctx*, double*, int64_t, int64_t, const double*, double*, int64_t, cudaStream_t);
 int lml_grad(Ctx*, const bgp_kernel_spec*, const double*, int64_t, int64_t, const double*, int64_t, const double*,
              double*, cudaStream_t);
@@ -542,6 +544,18 @@ int bgp_oz2_crt(bgp_ctx* c, const int32_t* G, int64_t M, int64_t N, const int32_
     CTX_OR_FAIL(c);
     if (M < 0 || N < 0 || (M > 0 && N > 0 && (!G || !ea || !eb || !C || ldc < N))) return BGP_E_ARG;
     return oz2_crt(ctx, G, M, N, ea, eb, alpha, C, ldc, (cudaStream_t)stream);
+}
+
+int64_t bgp_oz2_gemm_work_bytes(int64_t M, int64_t N, int64_t K) { return (M <= 0 || N <= 0 || K <= 0) ? 0 : oz2_gemm_work_bytes(M, N, K); }
+
+int bgp_oz2_gemm(bgp_ctx* c, int64_t M, int64_t N, int64_t K, double alpha, const double* A, int64_t lda, const double* B, int64_t ldb,
+                 double* C, int64_t ldc, void* work, int64_t work_bytes, void* stream) {
+    CTX_OR_FAIL(c);
+    if (M < 0 || N < 0 || K <= 0 || K % 64 || M > INT_MAX || N > INT_MAX) return BGP_E_ARG;
+    if (M == 0 || N == 0) return 0;
+    if (!A || !B || !C || !work || lda < K || ldb < K || ldc < N || work_bytes < oz2_gemm_work_bytes(M, N, K) || ((uintptr_t)work & 255))
+        return BGP_E_ARG;
+    return oz2_gemm(ctx, A, M, lda, B, N, ldb, K, alpha, C, ldc, work, (cudaStream_t)stream);
 }
 
 int bgp_potri(bgp_ctx* c, double* L, int64_t n, int64_t ldl, const double* dinv, double* work, int64_t ldw,

@@ -1,5 +1,6 @@
-// DRAFT -- NOT BUILT INTO libbattgp_b200.so (battgp_b200/build.py SOURCES does not list it) and never run on a GPU yet.
-// Compile check only:  nvcc -gencode arch=compute_100a,code=sm_100a -std=c++17 -I.. -c next/ozaki2_mma.cu
+// EXPERIMENTAL (bgp_oz2_gemm; not used by bgp_potrf).  Parity-green on the B200: bit-identical to tools/ozaki2_model.py
+// (tests/test_gpu_ozaki2_gemm.py); first timing, nothing tuned yet (profiles/probe_r01_oz2_gemm.jsonl): 8192^2 x 2048 at
+// 63.7 TF/s fp64-equivalent including residues + reconstruction (digit-plane kernel of ozaki.cu: 84.4, DMMA: 32.5).
 //
 // First (correctness-first, no multicast) form of the tensor-core kernel of the MODULAR int8 emulation (DESIGN.md section 5,
 // tools/ozaki2_model.py, csrc/ozaki2.cu): C'_j = A_j B_j^T for the 16 moduli, two moduli per TMEM pass, residues of the
@@ -14,7 +15,7 @@
 //   pass epilogue  : tcgen05.ld, t = acc mod p in [0,p), 32 bytes per thread and plane chunk -> T[plane][row][col] (uint8)
 //   reconstruction : oz2_crt_u8_kernel -- the arithmetic of oz2_crt_kernel (validated bit for bit against the model),
 //                    fed from T instead of int32 accumulators
-// Next steps once this form is parity-green: (1) 2x2 cluster with operand multicast (fill per modulus and k-step 24 -> 12 KB;
+// Next steps: (1) 2x2 cluster with operand multicast (fill per modulus and k-step 24 -> 12 KB;
 // without it the kernel moves as many bytes as ozaki.cu and stays L2-bound), (2) persistent tile loop with the TMEM drain
 // overlapped as in oz_mma_persistent_kernel, (3) fuse the reconstruction into the last pass.
 #include <climits>
@@ -358,4 +359,52 @@ crt_u8_kernel(const uint8_t* __restrict__ T, int64_t tm, int64_t tn, int M, int 
 // The byte therefore holds t for every modulus including 256 (t in [0, 255]).
 
 }  // namespace oz2draft
+
+void oz2_host_consts(uint32_t (&w)[16][4], uint32_t (&pl)[4], double (&wf)[16]);      // ozaki2.cu
+
+int64_t oz2_gemm_work_bytes(int64_t M, int64_t N, int64_t K) {
+    const int64_t mp = ((M + 127) / 128) * 128, np = ((N + 255) / 256) * 256;
+    return mp * K * 16 + np * K * 16 + (mp + np) * 4 + 1024 + 16 * mp * np + 1024;
+}
+
+// C[M,N] += alpha * A[M,K] B[N,K]^T through the modular scheme (K % 64 == 0; work >= oz2_gemm_work_bytes, 256-byte aligned)
+int oz2_gemm(Ctx* ctx, const double* A, int64_t M, int64_t lda, const double* B, int64_t N, int64_t ldb, int64_t K, double alpha,
+             double* C, int64_t ldc, void* work, cudaStream_t st) {
+    using namespace oz2draft;
+    if (M <= 0 || N <= 0) return 0;
+    if (K <= 0 || K % BK != 0 || K > (1 << 17)) return BGP_E_ARG;
+    const int64_t mp = ((M + 127) / 128) * 128, np = ((N + 255) / 256) * 256;
+    int8_t* pa = reinterpret_cast<int8_t*>(work);
+    int8_t* pb = pa + mp * K * 16;
+    int32_t* ea = reinterpret_cast<int32_t*>(pb + np * K * 16);
+    int32_t* eb = ea + mp;
+    uint8_t* T = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(eb + np) + 1023) & ~(uintptr_t)1023);
+    static thread_local uint64_t done = 0;
+    const uint64_t bit = 1ull << (ctx->device & 63);
+    constexpr int SMEM = STAGES * (A_STAGE + B_STAGE) + 1024 + 256;
+    if (!(done & bit)) {
+        Consts h = {};
+        oz2_host_consts(h.w, h.p, h.wf);
+        BGP_CUDA_OK(cudaMemcpyToSymbol(c_k, &h, sizeof(h)));
+        BGP_CUDA_OK(cudaFuncSetAttribute(mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
+        done |= bit;
+    }
+    slice_swz_kernel<<<(unsigned)(mp / 8), 512, 0, st>>>(A, M, K, lda, pa, ea, mp / 128);
+    BGP_LAUNCH_OK(ctx);
+    slice_swz_kernel<<<(unsigned)(np / 8), 512, 0, st>>>(B, N, K, ldb, pb, eb, np / 128);
+    BGP_LAUNCH_OK(ctx);
+    Args g;
+    g.sa = pa; g.nrb_a = mp / 128; g.arow0 = 0;
+    g.sb = pb; g.nrb_b = np / 128; g.brow0 = 0;
+    g.T = T; g.tm = mp; g.tn = np;
+    g.M = (int)M; g.N = (int)N; g.K = (int)K; g.tri = 0; g.roff = 0; g.coff = 0;
+    const int tiles_m = (int)(mp / 128), tiles_n = (int)(np / 256);
+    mma_kernel<<<tiles_m * tiles_n, 192, SMEM, st>>>(g, tiles_m, tiles_n);
+    BGP_LAUNCH_OK(ctx);
+    const int64_t nthreads = M * ((N + 3) / 4);
+    crt_u8_kernel<<<(unsigned)((nthreads + 255) / 256), 256, 0, st>>>(T, mp, np, (int)M, (int)N, ea, eb, alpha, C, ldc, 0, 0, 0);
+    BGP_LAUNCH_OK(ctx);
+    return 0;
+}
+
 }  // namespace bgp

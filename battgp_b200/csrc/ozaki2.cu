@@ -44,11 +44,22 @@ static double u160_to_double(const U160& a) {
     return r;
 }
 
+void oz2_host_consts(uint32_t (&w)[OZ2_NMOD][4], uint32_t (&pl)[4], double (&wf)[OZ2_NMOD]);
+
 static int oz2_upload_consts(Ctx* ctx) {
     static thread_local uint64_t done = 0;
     const uint64_t bit = 1ull << (ctx->device & 63);
     if (done & bit) return 0;
     Oz2Consts h = {};
+    oz2_host_consts(h.w, h.p, h.wf);
+    BGP_CUDA_OK(cudaMemcpyToSymbol(c_oz2, &h, sizeof(h)));
+    done |= bit;
+    return 0;
+}
+
+// CRT constants for the moduli above (host arithmetic on 160-bit integers)
+void oz2_host_consts(uint32_t (&w)[OZ2_NMOD][4], uint32_t (&pl)[4], double (&wf)[OZ2_NMOD]) {
+    struct { uint32_t (&w)[OZ2_NMOD][4]; uint32_t (&p)[4]; double (&wf)[OZ2_NMOD]; } h{w, pl, wf};
     U160 P = {{1, 0, 0, 0, 0}};
     for (int j = 0; j < OZ2_NMOD; j++) P = u160_mul_small(P, (uint32_t)oz2_modulus(j));
     for (int k = 0; k < 4; k++) h.p[k] = P.v[k];
@@ -65,9 +76,6 @@ static int oz2_upload_consts(Ctx* ctx) {
         for (int k = 0; k < 4; k++) h.w[j][k] = W.v[k];
         h.wf[j] = u160_to_double(W) / Pf;
     }
-    BGP_CUDA_OK(cudaMemcpyToSymbol(c_oz2, &h, sizeof(h)));
-    done |= bit;
-    return 0;
 }
 
 // ---- residues -------------------------------------------------------------------------------------------------------

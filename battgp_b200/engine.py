@@ -286,6 +286,20 @@ class Engine:
         _lib.check(rc, "bgp_oz2_crt")
         return C_
 
+    def oz2_gemm(self, A: torch.Tensor, B: torch.Tensor, C_: torch.Tensor, alpha: float = 1.0):
+        """EXPERIMENTAL: C += alpha * A B^T through the modular scheme end to end (csrc/next/ozaki2_mma.cu)."""
+        for t, nm in ((A, "A"), (B, "B"), (C_, "C")):
+            _check_f64_cuda(t, nm, self.device)
+        M, K = A.shape
+        N = B.shape[0]
+        need = int(self.L.bgp_oz2_gemm_work_bytes(M, N, K))
+        work = torch.empty(need + 256, dtype=torch.uint8, device=self.device)
+        off = (-work.data_ptr()) % 256
+        rc = self.L.bgp_oz2_gemm(self.h, M, N, K, float(alpha), _ptr(A), self._ld(A), _ptr(B), self._ld(B), _ptr(C_), self._ld(C_),
+                                 C.c_void_p(work.data_ptr() + off), need, self._stream())
+        _lib.check(rc, "bgp_oz2_gemm")
+        return C_
+
     # ------------------------------------------------------------------ K4
     def potrf(self, A: torch.Tensor):
         """In-place lower Cholesky.  ``A`` is n x n, or (n + mx) x n with mx extra right-hand-side rows that leave as

@@ -140,6 +140,12 @@ int bgp_oz_gemm(bgp_ctx* ctx, const void* bufA, int64_t rowsA, int64_t arow0, co
 int bgp_oz2_residues(bgp_ctx* ctx, const double* A, int64_t rows, int64_t K, int64_t ld, int8_t* residues, int32_t* expo, void* stream);
 int bgp_oz2_crt(bgp_ctx* ctx, const int32_t* G, int64_t M, int64_t N, const int32_t* ea, const int32_t* eb, double alpha, double* C,
                 int64_t ldc, void* stream);
+/* EXPERIMENTAL: C[M,N] += alpha A B^T through the modular scheme end to end (first, multicast-free form of its tensor-core
+ * kernel, csrc/next/ozaki2_mma.cu): residues -> 16 int8 products (128x256 tiles, two moduli per TMEM pass) -> reconstruction.
+ * K % 64 == 0; work: bgp_oz2_gemm_work_bytes bytes, 256-byte aligned. */
+int64_t bgp_oz2_gemm_work_bytes(int64_t M, int64_t N, int64_t K);
+int bgp_oz2_gemm(bgp_ctx* ctx, int64_t M, int64_t N, int64_t K, double alpha, const double* A, int64_t lda, const double* B, int64_t ldb,
+                 double* C, int64_t ldc, void* work, int64_t work_bytes, void* stream);
 
 /* ---- K4: Cholesky -------------------------------------------------------------------------------------
  * replaces torch.linalg.cholesky_ex inside GPyTorch's psd_safe_cholesky, reached from ExactGP.__call__

@@ -365,3 +365,16 @@ if "pdl" in what:
                               "potrs_vec_ms": round(bs, 4), "alpha_sum": float(al.sum()), "z_sq": float(z @ z)}), flush=True)
         eng.set("pdl", 1)
         del K
+if "oz2" in what:
+    # modular (CRT) int8 product, first multicast-free form, against the digit-plane kernel and the DMMA kernel
+    for (M, N, K) in ((4096, 4096, 2048), (8192, 8192, 2048), (8192, 8192, 512)):
+        A = torch.randn(M, K, dtype=torch.float64, device=dev); B = torch.randn(N, K, dtype=torch.float64, device=dev)
+        C1 = torch.zeros(M, N, dtype=torch.float64, device=dev); C2 = torch.zeros_like(C1); C3 = torch.zeros_like(C1)
+        ms2 = ev(lambda: eng.oz2_gemm(A, B, C1, alpha=-1.0), reps=3)
+        ms1 = ev(lambda: eng.gemm_nt_i8(A, B, C2, alpha=-1.0), reps=3)
+        ms0 = ev(lambda: eng.gemm_nt(A, B, C3, alpha=-1.0, beta=1.0), reps=3)
+        rel = float((C1 / 4 - C3 / 4).norm() / (C3 / 4).norm())
+        print(json.dumps({"op": "oz2_gemm", "M": M, "N": N, "K": K, "ms_modular_incl_slice_crt": round(ms2, 3), "ms_digitplanes_incl_slice": round(ms1, 3),
+                          "ms_dmma": round(ms0, 3), "tflops_equiv_modular": round(2 * M * N * K / ms2 * 1e-9, 2),
+                          "tflops_equiv_digitplanes": round(2 * M * N * K / ms1 * 1e-9, 2), "rel_diff_vs_dmma": rel}), flush=True)
+        del A, B, C1, C2, C3
