@@ -5,8 +5,8 @@
 //   oz2_residue_kernel : fp64 rows -> per-row scale exponent + symmetric int8 residues of trunc(a * 2^(BETA - e)) for the
 //                        16 moduli (plain [modulus][row][K] layout; the swizzled operand image comes with the MMA kernel)
 //   oz2_crt_kernel     : 16 int32 accumulators per element -> exact 128-bit integer -> double -> C += alpha * 2^(ea+eb-2 BETA) * C'
-// The tensor-core kernel that goes between them (256-wide cta_group::2 tiles, two moduli per TMEM pass) is the next round's
-// work; until then nothing in bgp_potrf uses these entry points (the tests drive them with an exact torch product between).
+// A first form of the tensor-core kernel that goes between them is next/ozaki2_mma.cu (bgp_oz2_gemm, experimental); bgp_potrf
+// does not use this scheme yet.
 #include <climits>
 #include "common.cuh"
 
