@@ -229,6 +229,13 @@ extern "C" {
 
 int bgp_version(void) { return BGP_VERSION; }
 void bgp_debug_leaf_clk(long long* out) { bgp::leaf_clk_read(out); }
+// diagnostics (tools/oz_timeline.py): CTA 0 of the int8 kernel writes 16 clock64 stamps per tile into buf (device, cap tiles)
+void bgp_debug_oz_timeline(bgp_ctx* p, long long* buf, int cap) {
+    if (!p) return;
+    Ctx* c = reinterpret_cast<Ctx*>(p);
+    c->oz_dbg = cap > 0 ? buf : nullptr;
+    c->oz_dbg_cap = cap > 0 ? cap : 0;
+}
 const char* bgp_last_error(void) { return g_err; }
 
 int bgp_grad_slots(const bgp_kernel_spec* s) {
@@ -304,6 +311,7 @@ int bgp_ctx_set(bgp_ctx* p, const char* key, int value) {
     }
     if (!strcmp(key, "ozaki")) { c->ozaki = value ? 1 : 0; return 0; }
     if (!strcmp(key, "oz_cluster")) { if (value != 1 && value != 2 && value != 4) return BGP_E_ARG; c->oz_cluster = value; return 0; }
+    if (!strcmp(key, "oz_group")) { if (value < 1 || value > 1024) return BGP_E_ARG; c->oz_group = value; return 0; }
     if (!strcmp(key, "oz_tpc")) { if (value < 0 || value > 4096) return BGP_E_ARG; c->oz_tpc = value; return 0; }
     if (!strcmp(key, "gemm_cfg")) { if (value < 0 || value > 7) return BGP_E_ARG; c->gemm_cfg = value; return 0; }
     return BGP_E_ARG;

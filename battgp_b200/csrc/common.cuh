@@ -37,6 +37,9 @@ struct Ctx {
     int64_t ws_bytes = 0;
     void* ws_trsm = nullptr;                // tail of ws used by the TRSM updates (set by bgp_potrf for its panels)
     int64_t ws_trsm_bytes = 0;
+    int oz_group = 8;                       // tile rows per raster group of the int8 kernel
+    long long* oz_dbg = nullptr;            // diagnostics: clock64 timeline of CTA 0 (bgp_debug_oz_timeline)
+    int oz_dbg_cap = 0;
     int gemm_cfg = 0;                       // 0 = default big-tile config, else forced variant (probing)
     int64_t launches = 0;
 };

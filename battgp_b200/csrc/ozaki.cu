@@ -1,19 +1,23 @@
-// FP64-accurate NT GEMM on the 5th-gen tensor cores by integer slicing (Ozaki scheme I) -- EXPERIMENTAL path.
+// FP64-accurate NT GEMM on the 5th-gen tensor cores by integer slicing (Ozaki scheme I).
 //
-// tcgen05 has no f64 kind, so the FP64 DMMA pipe (37 TF/s) bounds gemm_nt.cu.  Here every fp64 operand row is split
-// into 8 signed 7-bit digits against a per-row power-of-two scale,
-//     a = 2^e * ( d0/2^6 + d1/2^13 + ... + d7/2^55 ),   d_s in [-64, 64]  (exact: 55 bits + sign),
-// and  A B^T = sum_{s,t} 2^(eA_i + eB_j - 12 - 7(s+t)) (A_s B_t^T)  is evaluated with EXACT int8 x int8 -> int32
-// tcgen05.mma (kind::i8) products.  Pairs with s+t > 7 are dropped (<= K * 2^-56 relative to rowmax*colmax, the size of
-// fp64's own rounding), leaving 36 products whose partial sums with equal s+t share one int32 accumulator in TMEM
-// (8 accumulators x 64 columns = all 512 TMEM columns of a 128 x 64 tile).  The epilogue reads the 8 accumulators with
-// tcgen05.ld, recombines them in fp64 and applies C += alpha * (...).
+// tcgen05 has no f64 kind, so the FP64 DMMA pipe (37 TF/s) bounds gemm_nt.cu.  Here every fp64 operand row is scaled by a
+// power of two 2^e (row maximum), rounded to a 56-bit signed integer q = rint(a 2^(55-e)) and written in radix 256 with
+// SEVEN signed 8-bit digits (two's-complement radix-256: q = sum_s d_s 256^(6-s), d_s in [-128, 127] -- the digits are just
+// the bytes of q + 0x80..80 with their top bits flipped),
+//     a = 2^e * ( d0/2^7 + d1/2^15 + ... + d6/2^55 )            (55 bits + sign, every step exact),
+// and  A B^T = sum_{s,t} 2^(eA_i + eB_j - 14 - 8(s+t)) (A_s B_t^T)  is evaluated with EXACT int8 x int8 -> int32
+// tcgen05.mma (kind::i8) products.  Pairs with s+t > 6 are dropped (<= 6 K 2^-56 relative to rowscale*colscale, the size of
+// fp64's own rounding), leaving 28 products whose partial sums with equal s+t share one int32 accumulator in TMEM
+// (7 accumulators x 64 columns of a 128 x 64 tile; |sum| <= 7 K 2^14 < 2^31 for K <= OZ_MAX_K).  The epilogue reads the
+// accumulators with tcgen05.ld, recombines them in fp64 and applies C += alpha * (...).
+// (Round 1 used eight balanced 7-bit digits = 36 products for the same 55 bits.)
 //
-// Kernel structure (one 128x64 tile per CTA, 192 threads):
+// Kernel structure (persistent, 192 threads, one CTA per SM or a few tiles per CTA):
 //   warp 0  : producer   -- cp.async.bulk (TMA bulk engine) copies of pre-swizzled slice tiles into a 2-stage smem ring,
-//                           completion on mbarriers (expect_tx)
-//   warp 1  : MMA issuer -- one thread issues 72 tcgen05.mma per 64-wide k-block, tcgen05.commit frees the stage
-//   warps 2-5: epilogue  -- tcgen05.ld of the accumulators (one TMEM lane quadrant each), fp64 recombination, C update
+//                           completion on mbarriers (expect_tx); with clusters the A stage is multicast to the N-adjacent CTAs
+//   warp 1  : MMA issuer -- one elected lane issues 20 wide tcgen05.mma per 64-wide k-block, tcgen05.commit frees the stage
+//   warps 2-5: epilogue  -- software-pipelined tcgen05.ld of the accumulators (one TMEM lane quadrant each), fp64
+//                           recombination, TMEM released, then the C update (C was prefetched into L2 while the MMAs ran)
 // The slice kernel writes the operand slices to global memory already in the 64-byte-swizzled shared-memory image the
 // UMMA descriptors expect, in [k-block][128-row block][slice] order, so a tile's slices are contiguous bulk copies.
 #include <climits>
@@ -21,12 +25,14 @@
 
 namespace bgp {
 
-constexpr int OZ_S = 8;
+constexpr int OZ_S = 7;
 constexpr int OZ_BM = 128, OZ_BN = 64, OZ_BK = 64;
 constexpr int OZ_STAGES = 2;
-constexpr int OZ_A_STAGE = OZ_S * OZ_BM * OZ_BK;     // 65536 B
-constexpr int OZ_B_STAGE = OZ_S * OZ_BN * OZ_BK;     // 32768 B
+constexpr int OZ_A_STAGE = OZ_S * OZ_BM * OZ_BK;     // 57344 B
+constexpr int OZ_B_STAGE = OZ_S * OZ_BN * OZ_BK;     // 28672 B
 constexpr int OZ_SLICE_TILE = OZ_BM * OZ_BK;         // 8192 B: one slice of a 128-row block for one k-block
+constexpr int OZ_MAX_K = 16384;                      // 7 pairs * K * 2^14 must stay below 2^31
+constexpr long long OZ_DIGIT_BIAS = 0x0080808080808080ll;
 
 // ------------------------------------------------------------------------------------------------ slicing
 __device__ __forceinline__ int oz_swz64(int r8, int kb64) {
@@ -69,7 +75,10 @@ oz_slice_kernel(const double* __restrict__ P, int64_t rows, int64_t K, int64_t l
     const bool poisoned = (rb_bits >> 52) == 0x7FFull;                      // Inf or NaN somewhere in the row
     const double rowmax = __longlong_as_double((long long)rb_bits);
     int e = 0;
-    if (!poisoned && rowmax > 0.0) (void)frexp(rowmax, &e);                // rowmax = f * 2^e, f in [0.5, 1)
+    if (!poisoned && rowmax > 0.0) {
+        const double f = frexp(rowmax, &e);                                 // rowmax = f * 2^e, f in [0.5, 1)
+        if (f > 0.99) e += 1;                                               // digits reach +127/128 (1 + 1/256 + ...) = 0.996 only
+    }
     // row scale 2^e; NaN for a poisoned row, so that every product involving it comes out NaN like in fp64 arithmetic
     if (ct == 0 && row < nrb * 128) ex[row] = poisoned ? __longlong_as_double(0x7FF8000000000000ll) : scalbn(1.0, e);
     const int64_t rb = row >> 7;
@@ -82,16 +91,12 @@ oz_slice_kernel(const double* __restrict__ P, int64_t rows, int64_t K, int64_t l
             const double* p = P + srow * ld + c * 16;
 #pragma unroll
             for (int i = 0; i < 16; i++) {
-                double x = scalbn(p[i], -e);                              // |x| < 1, exact
-                double v = rint(x * 64.0);
-                w[0][i >> 2] |= ((uint32_t)(int)v & 255u) << ((i & 3) * 8);
-                x = fma(x, 64.0, -v);                                     // |x| <= 0.5, exact
+                // q = rint(a 2^(55-e)), |q| <= 0.99 2^55 (the scaling is exact; values below 2^(e-56) round to 0)
+                const long long q = __double2ll_rn(scalbn(p[i], 55 - e));
+                const unsigned long long dq = (unsigned long long)((q + OZ_DIGIT_BIAS) ^ OZ_DIGIT_BIAS);   // byte 6-s = digit s
 #pragma unroll
-                for (int s = 1; s < OZ_S; s++) {
-                    v = rint(x * 128.0);
-                    w[s][i >> 2] |= ((uint32_t)(int)v & 255u) << ((i & 3) * 8);
-                    x = fma(x, 128.0, -v);
-                }
+                for (int s = 0; s < OZ_S; s++)
+                    w[s][i >> 2] |= ((uint32_t)(dq >> (8 * (OZ_S - 1 - s))) & 255u) << ((i & 3) * 8);
             }
         }
         const int64_t kb = (c * 16) >> 6;
@@ -128,6 +133,10 @@ __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                  ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
 }
+__device__ __forceinline__ void bulk_g2s_mc(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar, uint16_t mask) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1], %2, [%3], %4;"
+                 ::"r"(dst), "l"(src), "r"(bytes), "r"(bar), "h"(mask) : "memory");
+}
 __device__ __forceinline__ uint64_t oz_desc(uint32_t saddr) {
     // K-major, SWIZZLE_64B (layout type 4), SBO = 512 B (8 rows x 64 B), LBO = 0, descriptor version 1 (sm_100)
     uint64_t d = 0;
@@ -145,7 +154,12 @@ __device__ __forceinline__ void oz_mma_i8(uint32_t tmem_d, uint64_t da, uint64_t
 __device__ __forceinline__ void oz_commit(uint32_t bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
-__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
+__device__ __forceinline__ void oz_commit_mc(uint32_t bar, uint16_t mask) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+                 ::"r"(bar), "h"(mask) : "memory");
+}
+// asynchronous TMEM load of 32 columns of this warp's lane quadrant; the registers are valid after tmem_ld_wait(v)
+__device__ __forceinline__ void tmem_ld32_async(uint32_t taddr, uint32_t (&v)[32]) {
     asm volatile("tcgen05.ld.sync.aligned.32x32b.x32.b32 "
                  "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
                  : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
@@ -153,8 +167,17 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
                    "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
                    "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
                  : "r"(taddr) : "memory");
-    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
+// waits for every outstanding tcgen05.ld of this thread; the "+r" operands tie the consumers of v to the wait
+__device__ __forceinline__ void tmem_ld_wait(uint32_t (&v)[32]) {
+    asm volatile("tcgen05.wait::ld.sync.aligned;"
+                 : "+r"(v[0]), "+r"(v[1]), "+r"(v[2]), "+r"(v[3]), "+r"(v[4]), "+r"(v[5]), "+r"(v[6]), "+r"(v[7]), "+r"(v[8]),
+                   "+r"(v[9]), "+r"(v[10]), "+r"(v[11]), "+r"(v[12]), "+r"(v[13]), "+r"(v[14]), "+r"(v[15]), "+r"(v[16]),
+                   "+r"(v[17]), "+r"(v[18]), "+r"(v[19]), "+r"(v[20]), "+r"(v[21]), "+r"(v[22]), "+r"(v[23]), "+r"(v[24]),
+                   "+r"(v[25]), "+r"(v[26]), "+r"(v[27]), "+r"(v[28]), "+r"(v[29]), "+r"(v[30]), "+r"(v[31])
+                 :: "memory");
+}
+__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 
 __device__ __forceinline__ bool elect_one() {
     uint32_t pred;
@@ -175,363 +198,19 @@ struct OzArgs {
     double alpha;
     int tri; int64_t roff, coff;
     int debug_noload;      // experiment: only the first OZ_STAGES k-blocks are really loaded
+    int group;             // raster: tile rows per group (oz_decode)
+    int64_t brb_max;       // last valid 128-row block of B (cluster tiles past N read a valid block; stores are masked)
+    long long* dbg;        // diagnostics: per-tile clock64 stamps of CTA 0 (bgp_debug_oz_timeline), 16 slots per tile
+    int dbg_cap;
 };
 
-__global__ void __launch_bounds__(192, 1) oz_mma_kernel(OzArgs g, int tiles_m, int tiles_n) {
-    // grouped raster as in gemm_nt.cu
-    constexpr int GROUP = 8;
-    const int pid = blockIdx.x;
-    const int per_group = GROUP * tiles_n;
-    const int gid = pid / per_group;
-    const int first_m = gid * GROUP;
-    const int gsize = min(tiles_m - first_m, GROUP);
-    const int tm = first_m + (pid % per_group) % gsize;
-    const int tn = (pid % per_group) / gsize;
-    const int m0 = tm * OZ_BM, n0 = tn * OZ_BN;
-    if (g.tri && ((int64_t)n0 + g.coff > (int64_t)m0 + OZ_BM - 1 + g.roff)) return;
-
-    extern __shared__ uint8_t oz_smem_raw[];
-    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(oz_smem_raw) + 1023) & ~(uintptr_t)1023);
-    uint8_t* sA = smem;                                       // [stage][8 slices][128 x 64 B]
-    uint8_t* sB = smem + OZ_STAGES * OZ_A_STAGE;              // [stage][8 slices][64 x 64 B]
-    uint64_t* bars = reinterpret_cast<uint64_t*>(sB + OZ_STAGES * OZ_B_STAGE);
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8);
-    const uint32_t full0 = smem_u32(bars), empty0 = smem_u32(bars + OZ_STAGES), tfull = smem_u32(bars + 2 * OZ_STAGES);
-
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    if (warp == 0 && lane == 0) {
-        for (int i = 0; i < OZ_STAGES; i++) { mbar_init(full0 + 8 * i, 1); mbar_init(empty0 + 8 * i, 1); }
-        mbar_init(tfull, 1);
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    }
-    if (warp == 1) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512) : "memory");
-        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-    }
-    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-    __syncthreads();
-    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-    const uint32_t tmem_base = *tmem_slot;
-    const int KB = g.K / OZ_BK;
-
-    // Producer and MMA warps run their loops warp-uniformly (all 32 lanes wait on the barriers, one elected lane
-    // issues): operands then live in uniform registers and no per-lane "waterfall" code is generated around UTCIMMA.
-    if (warp == 0) {
-        const int64_t arb = (g.arow0 + m0) >> 7;
-        const int64_t brb = (g.brow0 + n0) >> 7;
-        const int bhalf = (int)(((g.brow0 + n0) >> 6) & 1);
-        for (int kb = 0; kb < KB; kb++) {
-            const int st = kb % OZ_STAGES;
-            const uint32_t ph = (kb / OZ_STAGES) & 1;
-            mbar_wait(empty0 + 8 * st, ph ^ 1);
-            if (elect_one()) {
-                if (g.debug_noload && kb >= OZ_STAGES) {
-                    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(full0 + 8 * st) : "memory");
-                } else {
-                    mbar_expect_tx(full0 + 8 * st, OZ_A_STAGE + OZ_B_STAGE);
-                    bulk_g2s(smem_u32(sA + st * OZ_A_STAGE), g.sa + ((int64_t)kb * g.nrb_a + arb) * OZ_S * OZ_SLICE_TILE, OZ_A_STAGE,
-                             full0 + 8 * st);
-                    const int8_t* bsrc = g.sb + ((int64_t)kb * g.nrb_b + brb) * OZ_S * OZ_SLICE_TILE + bhalf * 4096;
-#pragma unroll
-                    for (int s = 0; s < OZ_S; s++)
-                        bulk_g2s(smem_u32(sB + st * OZ_B_STAGE + s * 4096), bsrc + (int64_t)s * OZ_SLICE_TILE, 4096, full0 + 8 * st);
-                }
-            }
-            __syncwarp();
-        }
-    } else if (warp == 1) {
-        // kind::i8, D = S32, A/B = signed int8, both K-major, M = 128.  For a fixed A slice s the B slices t = 0..7-s are
-        // adjacent 64-row tiles in shared memory AND their accumulators c = s+t are adjacent 64-column blocks in TMEM, so
-        // they are issued as ONE wide MMA (N up to 256): 12 instead of 36 instructions per k-step and, more importantly,
-        // each A slice is read from shared memory 1-2 times instead of 8-s times (the 128 B/cycle smem port, not the
-        // tensor pipe, limited the 36-MMA form).
-        const uint32_t idesc0 = (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(OZ_BM >> 4) << 24);
-        const uint64_t dzero = oz_desc(0);
-        for (int kb = 0; kb < KB; kb++) {
-            const int st = kb % OZ_STAGES;
-            const uint32_t ph = (kb / OZ_STAGES) & 1;
-            mbar_wait(full0 + 8 * st, ph);
-            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            if (elect_one()) {
-                const uint64_t da0 = dzero + (uint64_t)(smem_u32(sA + st * OZ_A_STAGE) >> 4);
-                const uint64_t db0 = dzero + (uint64_t)(smem_u32(sB + st * OZ_B_STAGE) >> 4);
-#pragma unroll
-                for (int ks = 0; ks < OZ_BK / 32; ks++) {
-#pragma unroll
-                    for (int s = 0; s < OZ_S; s++) {
-                        const uint64_t da = da0 + (uint64_t)((s * OZ_SLICE_TILE + ks * 32) >> 4);
-                        const uint32_t acc = (ks > 0 || s > 0) ? 1u : (kb > 0 ? 1u : 0u);
-#pragma unroll
-                        for (int t0 = 0; t0 + s < OZ_S; t0 += 4) {
-                            const int nt = (OZ_S - s - t0) < 4 ? (OZ_S - s - t0) : 4;     // B slices in this MMA
-                            const uint64_t db = db0 + (uint64_t)((t0 * 4096 + ks * 32) >> 4);
-                            const uint32_t idesc = idesc0 | ((uint32_t)((nt * OZ_BN) >> 3) << 17);
-                            oz_mma_i8(tmem_base + (uint32_t)(s + t0) * OZ_BN, da, db, idesc, acc);
-                        }
-                    }
-                }
-                oz_commit(empty0 + 8 * st);
-                if (kb == KB - 1) oz_commit(tfull);
-            }
-            __syncwarp();
-        }
-    } else {
-        mbar_wait(tfull, 0);
-        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        // All MMAs have completed (tfull), so the operand stages are idle: each epilogue warp uses 32 x 33 doubles of
-        // them to transpose its 32-row x 32-column block -- TMEM hands a thread one ROW (lane), global memory wants a
-        // warp on one row segment (256 contiguous bytes).
-        const int q = warp & 3;                                   // TMEM lane quadrant this warp may read
-        double* tbuf = reinterpret_cast<double*>(sA) + (warp - 2) * (32 * 33);
-        const int row_l = q * 32 + lane;
-        const double sa = (m0 + row_l < g.M) ? g.alpha * g.exa[g.arow0 + m0 + row_l] * (1.0 / 4096.0) : 0.0;
-#pragma unroll 1
-        for (int h = 0; h < OZ_BN / 32; h++) {
-            double acc[32];
-#pragma unroll
-            for (int j = 0; j < 32; j++) acc[j] = 0.0;
-            double w = 1.0;
-#pragma unroll 1
-            for (int c = 0; c < OZ_S; c++) {
-                uint32_t v[32];
-                tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(c * OZ_BN + h * 32), v);
-#pragma unroll
-                for (int j = 0; j < 32; j++) acc[j] = fma(i32_to_f64(v[j]), w, acc[j]);
-                w *= (1.0 / 128.0);
-            }
-#pragma unroll
-            for (int j = 0; j < 32; j++) tbuf[lane * 33 + j] = acc[j] * sa;     // row scale applied here
-            __syncwarp();
-            // now lane = column
-            const int col = n0 + h * 32 + lane;
-            const bool cok = col < g.N;
-            const double sb = cok ? g.exb[g.brow0 + col] : 0.0;
-            // 32 independent coalesced loads in flight, then the dependent stores
-            double cold[32];
-            unsigned okmask = 0;
-#pragma unroll
-            for (int r = 0; r < 32; r++) {
-                const int row = m0 + q * 32 + r;
-                const bool ok = row < g.M && cok && (!g.tri || ((int64_t)col + g.coff <= (int64_t)row + g.roff));
-                okmask |= ok ? (1u << r) : 0u;
-                cold[r] = ok ? g.C[(int64_t)row * g.ldc + col] : 0.0;
-            }
-#pragma unroll
-            for (int r = 0; r < 32; r++)
-                if ((okmask >> r) & 1u) g.C[(int64_t)(m0 + q * 32 + r) * g.ldc + col] = cold[r] + tbuf[r * 33 + lane] * sb;
-            __syncwarp();
-        }
-    }
-    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-    __syncthreads();
-    if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
-}
-
-// ------------------------------------------------------------------------------------------------ persistent variant
-// One CTA per SM loops over the (lower-triangular) tiles.  The three roles run decoupled pipelines:
-//   producer  : keeps the 2-stage operand ring full ACROSS tile boundaries (the next tile's first k-blocks are already in
-//               flight while the current tile is in its epilogue),
-//   MMA issuer: waits for the epilogue to have drained TMEM (tmem_empty), then issues the tile's k-loop,
-//   epilogue  : prefetches the C tile while the MMAs run, drains the 8 accumulators with tcgen05.ld, releases TMEM
-//               (tmem_empty) and only then does the C read-modify-write -- so stores overlap the next tile's MMAs.
-// Removes the per-tile launch / TMEM-alloc / barrier-init / pipeline-fill / C-latency cost of the one-tile-per-CTA form.
-constexpr int OZ_TBUF = 32 * 33;                  // doubles per epilogue warp
-
-__device__ __forceinline__ bool oz_decode_tile(const OzArgs& g, int pid, int tiles_m, int tiles_n, int& m0, int& n0) {
-    constexpr int GROUP = 8;
-    const int per_group = GROUP * tiles_n;
-    const int gid = pid / per_group;
-    const int first_m = gid * GROUP;
-    const int gsize = min(tiles_m - first_m, GROUP);
-    const int tm = first_m + (pid % per_group) % gsize;
-    const int tn = (pid % per_group) / gsize;
-    m0 = tm * OZ_BM;
-    n0 = tn * OZ_BN;
-    return !(g.tri && ((int64_t)n0 + g.coff > (int64_t)m0 + OZ_BM - 1 + g.roff));
-}
-
-__global__ void __launch_bounds__(192, 1) oz_mma_persistent_kernel(OzArgs g, int tiles_m, int tiles_n, int tiles_per_cta) {
-    // this CTA owns raster positions [pid_begin, pid_end); leave before touching TMEM if none of them is a real tile
-    // tiles_per_cta > 0: consecutive raster positions;  tiles_per_cta == 0: grid-stride (fully persistent, one CTA per SM;
-    // concurrently running CTAs then work on neighbouring tiles and share operand panels in L2)
-    const int total = tiles_m * tiles_n;
-    const int pid_step = tiles_per_cta > 0 ? 1 : (int)gridDim.x;
-    const int pid_begin = tiles_per_cta > 0 ? blockIdx.x * tiles_per_cta : (int)blockIdx.x;
-    const int pid_end = tiles_per_cta > 0 ? min(total, pid_begin + tiles_per_cta) : total;
-    {
-        bool any = false;
-        for (int pid = pid_begin; pid < pid_end && !any; pid += pid_step) { int a, b; any = oz_decode_tile(g, pid, tiles_m, tiles_n, a, b); }
-        if (!any) return;
-    }
-    extern __shared__ uint8_t oz_smem_raw[];
-    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(oz_smem_raw) + 1023) & ~(uintptr_t)1023);
-    uint8_t* sA = smem;
-    uint8_t* sB = smem + OZ_STAGES * OZ_A_STAGE;
-    double* tbuf_all = reinterpret_cast<double*>(sB + OZ_STAGES * OZ_B_STAGE);
-    uint64_t* bars = reinterpret_cast<uint64_t*>(tbuf_all + 4 * OZ_TBUF);
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8);
-    const uint32_t full0 = smem_u32(bars), empty0 = smem_u32(bars + OZ_STAGES);
-    const uint32_t tfull = smem_u32(bars + 2 * OZ_STAGES), tempty = smem_u32(bars + 2 * OZ_STAGES + 1);
-
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    if (warp == 0 && lane == 0) {
-        for (int i = 0; i < OZ_STAGES; i++) { mbar_init(full0 + 8 * i, 1); mbar_init(empty0 + 8 * i, 1); }
-        mbar_init(tfull, 1);
-        mbar_init(tempty, 4);                                   // one arrival per epilogue warp
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    }
-    if (warp == 1) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512) : "memory");
-        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-    }
-    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-    __syncthreads();
-    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-    const uint32_t tmem_base = *tmem_slot;
-    const int KB = g.K / OZ_BK;
-
-    if (warp == 0) {
-        uint32_t it = 0;                                        // k-block counter across tiles
-        for (int pid = pid_begin; pid < pid_end; pid += pid_step) {
-            int m0, n0;
-            if (!oz_decode_tile(g, pid, tiles_m, tiles_n, m0, n0)) continue;
-            const int64_t arb = (g.arow0 + m0) >> 7;
-            const int64_t brb = (g.brow0 + n0) >> 7;
-            const int bhalf = (int)(((g.brow0 + n0) >> 6) & 1);
-            for (int kb = 0; kb < KB; kb++, it++) {
-                const int st = it % OZ_STAGES;
-                const uint32_t ph = (it / OZ_STAGES) & 1;
-                mbar_wait(empty0 + 8 * st, ph ^ 1);
-                if (elect_one()) {
-                    mbar_expect_tx(full0 + 8 * st, OZ_A_STAGE + OZ_B_STAGE);
-                    bulk_g2s(smem_u32(sA + st * OZ_A_STAGE), g.sa + ((int64_t)kb * g.nrb_a + arb) * OZ_S * OZ_SLICE_TILE, OZ_A_STAGE,
-                             full0 + 8 * st);
-                    const int8_t* bsrc = g.sb + ((int64_t)kb * g.nrb_b + brb) * OZ_S * OZ_SLICE_TILE + bhalf * 4096;
-#pragma unroll
-                    for (int s = 0; s < OZ_S; s++)
-                        bulk_g2s(smem_u32(sB + st * OZ_B_STAGE + s * 4096), bsrc + (int64_t)s * OZ_SLICE_TILE, 4096, full0 + 8 * st);
-                }
-                __syncwarp();
-            }
-        }
-    } else if (warp == 1) {
-        const uint32_t idesc0 = (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(OZ_BM >> 4) << 24);
-        const uint64_t dzero = oz_desc(0);
-        uint32_t it = 0, tile_it = 0;
-        for (int pid = pid_begin; pid < pid_end; pid += pid_step) {
-            int m0, n0;
-            if (!oz_decode_tile(g, pid, tiles_m, tiles_n, m0, n0)) continue;
-            mbar_wait(tempty, (tile_it & 1) ^ 1);                // epilogue has drained the previous tile's accumulators
-            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            for (int kb = 0; kb < KB; kb++, it++) {
-                const int st = it % OZ_STAGES;
-                const uint32_t ph = (it / OZ_STAGES) & 1;
-                mbar_wait(full0 + 8 * st, ph);
-                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                if (elect_one()) {
-                    const uint64_t da0 = dzero + (uint64_t)(smem_u32(sA + st * OZ_A_STAGE) >> 4);
-                    const uint64_t db0 = dzero + (uint64_t)(smem_u32(sB + st * OZ_B_STAGE) >> 4);
-#pragma unroll
-                    for (int ks = 0; ks < OZ_BK / 32; ks++) {
-#pragma unroll
-                        for (int s = 0; s < OZ_S; s++) {
-                            const uint64_t da = da0 + (uint64_t)((s * OZ_SLICE_TILE + ks * 32) >> 4);
-                            const uint32_t acc = (ks > 0 || s > 0) ? 1u : (kb > 0 ? 1u : 0u);
-#pragma unroll
-                            for (int t0 = 0; t0 + s < OZ_S; t0 += 4) {
-                                const int nt = (OZ_S - s - t0) < 4 ? (OZ_S - s - t0) : 4;
-                                const uint64_t db = db0 + (uint64_t)((t0 * 4096 + ks * 32) >> 4);
-                                const uint32_t idesc = idesc0 | ((uint32_t)((nt * OZ_BN) >> 3) << 17);
-                                oz_mma_i8(tmem_base + (uint32_t)(s + t0) * OZ_BN, da, db, idesc, acc);
-                            }
-                        }
-                    }
-                    oz_commit(empty0 + 8 * st);
-                    if (kb == KB - 1) oz_commit(tfull);
-                }
-                __syncwarp();
-            }
-            tile_it++;
-        }
-    } else {
-        const int q = warp & 3;
-        double* tbuf = tbuf_all + (warp - 2) * OZ_TBUF;
-        uint32_t tile_it = 0;
-        for (int pid = pid_begin; pid < pid_end; pid += pid_step) {
-            int m0, n0;
-            if (!oz_decode_tile(g, pid, tiles_m, tiles_n, m0, n0)) continue;
-            const int row_l = q * 32 + lane;
-            const double sa = (m0 + row_l < g.M) ? g.alpha * g.exa[g.arow0 + m0 + row_l] * (1.0 / 4096.0) : 0.0;
-            // prefetch the C values this lane will update (lane = column within a 32-wide half, r = row of the quadrant)
-            double cold[2][32];
-            unsigned okmask[2];
-            double sb[2];
-#pragma unroll
-            for (int h = 0; h < 2; h++) {
-                const int col = n0 + h * 32 + lane;
-                const bool cok = col < g.N;
-                sb[h] = cok ? g.exb[g.brow0 + col] : 0.0;
-                okmask[h] = 0;
-#pragma unroll
-                for (int r = 0; r < 32; r++) {
-                    const int row = m0 + q * 32 + r;
-                    const bool ok = row < g.M && cok && (!g.tri || ((int64_t)col + g.coff <= (int64_t)row + g.roff));
-                    okmask[h] |= ok ? (1u << r) : 0u;
-                    cold[h][r] = ok ? g.C[(int64_t)row * g.ldc + col] : 0.0;
-                }
-            }
-            mbar_wait(tfull, tile_it & 1);
-            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-#pragma unroll
-            for (int h = 0; h < 2; h++) {
-                double acc[32];
-#pragma unroll
-                for (int j = 0; j < 32; j++) acc[j] = 0.0;
-                double w = 1.0;
-#pragma unroll 1
-                for (int c = 0; c < OZ_S; c++) {
-                    uint32_t v[32];
-                    tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(c * OZ_BN + h * 32), v);
-#pragma unroll
-                    for (int j = 0; j < 32; j++) acc[j] = fma(i32_to_f64(v[j]), w, acc[j]);
-                    w *= (1.0 / 128.0);
-                }
-                if (h == 1) {
-                    // all TMEM reads of this warp are done: let the MMA warp start the next tile
-                    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-                    __syncwarp();
-                    if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(tempty) : "memory");
-                }
-#pragma unroll
-                for (int j = 0; j < 32; j++) tbuf[lane * 33 + j] = acc[j] * sa;
-                __syncwarp();
-                const int col = n0 + h * 32 + lane;
-#pragma unroll
-                for (int r = 0; r < 32; r++)
-                    if ((okmask[h] >> r) & 1u) g.C[(int64_t)(m0 + q * 32 + r) * g.ldc + col] = cold[h][r] + tbuf[r * 33 + lane] * sb[h];
-                __syncwarp();
-            }
-            tile_it++;
-        }
-    }
-    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-    __syncthreads();
-    if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
-}
-
-__device__ __forceinline__ void bulk_g2s_mc(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar, uint16_t mask) {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1], %2, [%3], %4;"
-                 ::"r"(dst), "l"(src), "r"(bytes), "r"(bar), "h"(mask) : "memory");
-}
-__device__ __forceinline__ void oz_commit_mc(uint32_t bar, uint16_t mask) {
-    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
-                 ::"r"(bar), "h"(mask) : "memory");
-}
-// group raster: pid -> (tile row, group of CS tile columns); this CTA's own tile is column group*CS + rank.  A group is
-// skipped when its FIRST tile is above the diagonal; the other CTAs of a live group always run (their stores are masked).
+// Grouped raster over (tile row, group of CS tile columns): consecutive positions walk down `group` tile rows, then move one
+// column group to the right, so concurrently running CTAs share A row panels and B column panels in L2.  This CTA's own tile
+// is column tng*CS + rank.  A position is skipped when its FIRST tile lies above the diagonal (tri); the other CTAs of a
+// live cluster position always run (their stores are masked).
 template <int CS>
-__device__ __forceinline__ bool oz_decode_group(const OzArgs& g, int pid, int tiles_m, int tiles_ng, int rank, int& m0, int& n0) {
-    constexpr int GROUP = 8;
+__device__ __forceinline__ bool oz_decode(const OzArgs& g, int pid, int tiles_m, int tiles_ng, int rank, int& m0, int& n0) {
+    const int GROUP = g.group;
     const int per_group = GROUP * tiles_ng;
     const int gid = pid / per_group;
     const int first_m = gid * GROUP;
@@ -544,27 +223,37 @@ __device__ __forceinline__ bool oz_decode_group(const OzArgs& g, int pid, int ti
     return !(g.tri && ((int64_t)nfirst + g.coff > (int64_t)m0 + OZ_BM - 1 + g.roff));
 }
 
-// Cluster variant: CS CTAs (consecutive N tiles of the same tile row) share the A operand.  Each CTA loads 1/CS of the A
-// stage and MULTICASTS it to the whole cluster (cp.async.bulk ... .multicast::cluster), so the L2 -> SM traffic per CTA and
-// stage drops from 96 KB to 32 KB + 64/CS KB -- the one-CTA form is L2-bandwidth bound (~7.5 TB/s) at every K.
-// A stage may only be overwritten once EVERY CTA of the cluster has consumed it: the MMA warps commit with a multicast
-// arrive on the `empty` barriers of all CS CTAs (count = CS).  Fully persistent, grid-stride over groups of CS tiles.
+constexpr int OZ_TBUF = 32 * 33;                  // doubles per epilogue warp (32 x 32 transpose, padded)
+// diagnostics: CTA 0 stamps clock64 per tile (slot layout in tools/oz_probe.py)
+#define OZ_STAMP(slot) do { if (dbg_on && lane == 0 && tile_it < (uint32_t)g.dbg_cap) g.dbg[(size_t)tile_it * 16 + (slot)] = clock64(); } while (0)
+
+// The tile loop.  CS = 1: plain persistent CTA (tiles_per_cta > 0: consecutive raster positions, so CTAs keep retiring and the
+// high-priority panel stream of the look-ahead Cholesky finds free SMs; tiles_per_cta == 0: grid-stride, one CTA per SM).
+// CS = 2 / 4: clusters of N-adjacent CTAs share the A operand -- each CTA loads 1/CS of the A stage and MULTICASTS it to the
+// whole cluster, so the L2 -> SM traffic per CTA and k-block drops from 84 KB to 28 + 56/CS KB.  A stage may only be
+// overwritten once EVERY CTA of the cluster has consumed it: the MMA warps commit with a multicast arrive on the `empty`
+// barriers of all CS CTAs (count = CS).  Always grid-stride.
 template <int CS>
-__global__ void __launch_bounds__(192, 1) oz_mma_cluster_kernel(OzArgs g, int tiles_m, int tiles_n, int64_t brb_max) {
-    uint32_t crank;
-    asm volatile("mov.u32 %0, %cluster_ctarank;" : "=r"(crank));
-    const int tiles_ng = (tiles_n + CS - 1) / CS;               // tile groups per tile row
-    const int ncl = gridDim.x / CS, cid = blockIdx.x / CS;
-    const int tiles_per_cta = 0;
-    (void)tiles_per_cta;
-    // this CTA owns raster positions [pid_begin, pid_end); leave before touching TMEM if none of them is a real tile
+__global__ void __launch_bounds__(192, 1) oz_mma_kernel(OzArgs g, int tiles_m, int tiles_n, int tiles_per_cta) {
+    uint32_t crank = 0;
+    if (CS > 1) asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(crank));
+    const int tiles_ng = (tiles_n + CS - 1) / CS;               // column groups per tile row
     const int total = tiles_m * tiles_ng;
-    const int pid_step = ncl, pid_begin = cid, pid_end = total;
-    // every CTA of a cluster runs the same group sequence (no early exit: peers multicast into this CTA's smem)
+    const int ncl = (int)gridDim.x / CS, cid = (int)blockIdx.x / CS;
+    const int pid_step = (CS == 1 && tiles_per_cta > 0) ? 1 : ncl;
+    const int pid_begin = (CS == 1 && tiles_per_cta > 0) ? cid * tiles_per_cta : cid;
+    const int pid_end = (CS == 1 && tiles_per_cta > 0) ? min(total, pid_begin + tiles_per_cta) : total;
+    if (CS == 1) {
+        // leave before touching TMEM if none of this CTA's positions is a real tile (cluster CTAs never leave early:
+        // peers multicast into their shared memory)
+        bool any = false;
+        for (int pid = pid_begin; pid < pid_end && !any; pid += pid_step) { int a, b; any = oz_decode<CS>(g, pid, tiles_m, tiles_ng, 0, a, b); }
+        if (!any) return;
+    }
     extern __shared__ uint8_t oz_smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(oz_smem_raw) + 1023) & ~(uintptr_t)1023);
-    uint8_t* sA = smem;
-    uint8_t* sB = smem + OZ_STAGES * OZ_A_STAGE;
+    uint8_t* sA = smem;                                       // [stage][7 slices][128 x 64 B]
+    uint8_t* sB = smem + OZ_STAGES * OZ_A_STAGE;              // [stage][7 slices][64 x 64 B]
     double* tbuf_all = reinterpret_cast<double*>(sB + OZ_STAGES * OZ_B_STAGE);
     uint64_t* bars = reinterpret_cast<uint64_t*>(tbuf_all + 4 * OZ_TBUF);
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8);
@@ -584,51 +273,73 @@ __global__ void __launch_bounds__(192, 1) oz_mma_cluster_kernel(OzArgs g, int ti
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
-    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");   // peers' barriers are initialised
+    if (CS > 1) asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");   // peers' barriers are initialised
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem_base = *tmem_slot;
     const int KB = g.K / OZ_BK;
+    const bool dbg_on = g.dbg != nullptr && blockIdx.x == 0;
 
+    // Producer and MMA warps run their loops warp-uniformly (all 32 lanes wait on the barriers, one elected lane
+    // issues): operands then live in uniform registers and no per-lane "waterfall" code is generated around UTCIMMA.
     if (warp == 0) {
-        uint32_t it = 0;                                        // k-block counter across tiles
+        uint32_t it = 0, tile_it = 0;                           // k-block counter across tiles
         for (int pid = pid_begin; pid < pid_end; pid += pid_step) {
             int m0, n0;
-            if (!oz_decode_group<CS>(g, pid, tiles_m, tiles_ng, (int)crank, m0, n0)) continue;
+            if (!oz_decode<CS>(g, pid, tiles_m, tiles_ng, (int)crank, m0, n0)) continue;
+            OZ_STAMP(8);
             const int64_t arb = (g.arow0 + m0) >> 7;
-            const int64_t brb = min((g.brow0 + n0) >> 7, brb_max);   // tiles past N (odd tile count) read a valid block; stores are masked
+            const int64_t brb = min((g.brow0 + n0) >> 7, g.brb_max);
             const int bhalf = (int)(((g.brow0 + n0) >> 6) & 1);
             for (int kb = 0; kb < KB; kb++, it++) {
                 const int st = it % OZ_STAGES;
                 const uint32_t ph = (it / OZ_STAGES) & 1;
                 mbar_wait(empty0 + 8 * st, ph ^ 1);
                 if (elect_one()) {
-                    mbar_expect_tx(full0 + 8 * st, OZ_A_STAGE + OZ_B_STAGE);
-                    constexpr int APART = OZ_A_STAGE / CS;          // this CTA's share of the A stage, delivered to all CS CTAs
-                    bulk_g2s_mc(smem_u32(sA + st * OZ_A_STAGE + crank * APART),
-                                g.sa + ((int64_t)kb * g.nrb_a + arb) * OZ_S * OZ_SLICE_TILE + (int64_t)crank * APART, APART,
-                                full0 + 8 * st, (uint16_t)((1u << CS) - 1));
-                    const int8_t* bsrc = g.sb + ((int64_t)kb * g.nrb_b + brb) * OZ_S * OZ_SLICE_TILE + bhalf * 4096;
+                    if (CS == 1 && g.debug_noload && it >= OZ_STAGES) {
+                        asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(full0 + 8 * st) : "memory");
+                    } else {
+                        mbar_expect_tx(full0 + 8 * st, OZ_A_STAGE + OZ_B_STAGE);
+                        const int8_t* asrc = g.sa + ((int64_t)kb * g.nrb_a + arb) * OZ_S * OZ_SLICE_TILE;
+                        if (CS == 1) {
+                            bulk_g2s(smem_u32(sA + st * OZ_A_STAGE), asrc, OZ_A_STAGE, full0 + 8 * st);
+                        } else {
+                            constexpr int APART = OZ_A_STAGE / CS;  // this CTA's share of the A stage, delivered to all CS CTAs
+                            bulk_g2s_mc(smem_u32(sA + st * OZ_A_STAGE + crank * APART), asrc + (int64_t)crank * APART, APART,
+                                        full0 + 8 * st, (uint16_t)((1u << CS) - 1));
+                        }
+                        const int8_t* bsrc = g.sb + ((int64_t)kb * g.nrb_b + brb) * OZ_S * OZ_SLICE_TILE + bhalf * 4096;
 #pragma unroll
-                    for (int s = 0; s < OZ_S; s++)
-                        bulk_g2s(smem_u32(sB + st * OZ_B_STAGE + s * 4096), bsrc + (int64_t)s * OZ_SLICE_TILE, 4096, full0 + 8 * st);
+                        for (int s = 0; s < OZ_S; s++)
+                            bulk_g2s(smem_u32(sB + st * OZ_B_STAGE + s * 4096), bsrc + (int64_t)s * OZ_SLICE_TILE, 4096, full0 + 8 * st);
+                    }
                 }
                 __syncwarp();
             }
+            OZ_STAMP(9);
+            tile_it++;
         }
     } else if (warp == 1) {
+        // kind::i8, D = S32, A/B = signed int8, both K-major, M = 128.  For a fixed A slice s the B slices t = 0..6-s are
+        // adjacent 64-row tiles in shared memory AND their accumulators c = s+t are adjacent 64-column blocks in TMEM, so
+        // they are issued as ONE wide MMA (N up to 256): 10 instead of 28 instructions per k-step and, more importantly,
+        // each A slice is read from shared memory 1-2 times instead of 7-s times (the 128 B/cycle smem port, not the
+        // tensor pipe, limits narrow MMAs: tools/microbench/i8_peak.cu).
         const uint32_t idesc0 = (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(OZ_BM >> 4) << 24);
         const uint64_t dzero = oz_desc(0);
         uint32_t it = 0, tile_it = 0;
         for (int pid = pid_begin; pid < pid_end; pid += pid_step) {
             int m0, n0;
-            if (!oz_decode_group<CS>(g, pid, tiles_m, tiles_ng, (int)crank, m0, n0)) continue;
+            if (!oz_decode<CS>(g, pid, tiles_m, tiles_ng, (int)crank, m0, n0)) continue;
+            OZ_STAMP(0);
             mbar_wait(tempty, (tile_it & 1) ^ 1);                // epilogue has drained the previous tile's accumulators
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            OZ_STAMP(1);
             for (int kb = 0; kb < KB; kb++, it++) {
                 const int st = it % OZ_STAGES;
                 const uint32_t ph = (it / OZ_STAGES) & 1;
                 mbar_wait(full0 + 8 * st, ph);
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                if (kb == 0) OZ_STAMP(2);
                 if (elect_one()) {
                     const uint64_t da0 = dzero + (uint64_t)(smem_u32(sA + st * OZ_A_STAGE) >> 4);
                     const uint64_t db0 = dzero + (uint64_t)(smem_u32(sB + st * OZ_B_STAGE) >> 4);
@@ -640,84 +351,95 @@ __global__ void __launch_bounds__(192, 1) oz_mma_cluster_kernel(OzArgs g, int ti
                             const uint32_t acc = (ks > 0 || s > 0) ? 1u : (kb > 0 ? 1u : 0u);
 #pragma unroll
                             for (int t0 = 0; t0 + s < OZ_S; t0 += 4) {
-                                const int nt = (OZ_S - s - t0) < 4 ? (OZ_S - s - t0) : 4;
+                                const int nt = (OZ_S - s - t0) < 4 ? (OZ_S - s - t0) : 4;     // B slices in this MMA
                                 const uint64_t db = db0 + (uint64_t)((t0 * 4096 + ks * 32) >> 4);
                                 const uint32_t idesc = idesc0 | ((uint32_t)((nt * OZ_BN) >> 3) << 17);
                                 oz_mma_i8(tmem_base + (uint32_t)(s + t0) * OZ_BN, da, db, idesc, acc);
                             }
                         }
                     }
-                    oz_commit_mc(empty0 + 8 * st, (uint16_t)((1u << CS) - 1));
+                    if (CS == 1) oz_commit(empty0 + 8 * st);
+                    else oz_commit_mc(empty0 + 8 * st, (uint16_t)((1u << CS) - 1));
                     if (kb == KB - 1) oz_commit(tfull);
                 }
                 __syncwarp();
             }
+            OZ_STAMP(3);
             tile_it++;
         }
     } else {
-        const int q = warp & 3;
+        const int q = warp & 3;                                   // TMEM lane quadrant this warp may read
         double* tbuf = tbuf_all + (warp - 2) * OZ_TBUF;
         uint32_t tile_it = 0;
         for (int pid = pid_begin; pid < pid_end; pid += pid_step) {
             int m0, n0;
-            if (!oz_decode_group<CS>(g, pid, tiles_m, tiles_ng, (int)crank, m0, n0)) continue;
+            if (!oz_decode<CS>(g, pid, tiles_m, tiles_ng, (int)crank, m0, n0)) continue;
             const int row_l = q * 32 + lane;
-            const double sa = (m0 + row_l < g.M) ? g.alpha * g.exa[g.arow0 + m0 + row_l] * (1.0 / 4096.0) : 0.0;
-            // prefetch the C values this lane will update (lane = column within a 32-wide half, r = row of the quadrant)
-            double cold[2][32];
-            unsigned okmask[2];
-            double sb[2];
+            const double sa = (m0 + row_l < g.M) ? g.alpha * g.exa[g.arow0 + m0 + row_l] * (1.0 / 16384.0) : 0.0;
+            // pull this warp's 32 x 64 block of C towards L2 while the MMAs of the tile run (lane = row, 4 lines of 128 B)
+            if (m0 + row_l < g.M) {
+                const double* crow = g.C + (int64_t)(m0 + row_l) * g.ldc + n0;
+#pragma unroll
+                for (int i = 0; i < 4; i++)
+                    if (n0 + i * 16 < g.N && (!g.tri || ((int64_t)n0 + i * 16 + g.coff <= (int64_t)m0 + row_l + g.roff))) prefetch_l2(crow + i * 16);
+            }
+            if (warp == 2) OZ_STAMP(4);
+            mbar_wait(tfull, tile_it & 1);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            if (warp == 2) OZ_STAMP(5);
+            // drain: 2 column halves x 7 accumulators, the TMEM load of step i+1 in flight while step i is recombined
+            double acc[2][32];
+            uint32_t v[2][32];
+            const uint32_t tq = tmem_base + ((uint32_t)(q * 32) << 16);
+            tmem_ld32_async(tq, v[0]);
+#pragma unroll
+            for (int i = 0; i < 2 * OZ_S; i++) {
+                const int h = i / OZ_S, c = i % OZ_S;
+                tmem_ld_wait(v[i & 1]);
+                if (i + 1 < 2 * OZ_S) tmem_ld32_async(tq + (uint32_t)(((i + 1) % OZ_S) * OZ_BN + ((i + 1) / OZ_S) * 32), v[(i + 1) & 1]);
+                const double w = 1.0 / (double)(1ull << (8 * c));
+#pragma unroll
+                for (int j = 0; j < 32; j++) {
+                    const double x = i32_to_f64(v[i & 1][j]);
+                    acc[h][j] = (c == 0) ? x : fma(x, w, acc[h][j]);
+                }
+            }
+            // all TMEM reads of this warp are done: let the MMA warp start the next tile
+            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+            __syncwarp();
+            if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(tempty) : "memory");
+            if (warp == 2) OZ_STAMP(6);
 #pragma unroll
             for (int h = 0; h < 2; h++) {
+                // TMEM hands a thread one ROW (lane), global memory wants a warp on one row segment: transpose through smem
+#pragma unroll
+                for (int j = 0; j < 32; j++) tbuf[lane * 33 + j] = acc[h][j] * sa;     // row scale applied here
+                __syncwarp();
+                // now lane = column
                 const int col = n0 + h * 32 + lane;
                 const bool cok = col < g.N;
-                sb[h] = cok ? g.exb[g.brow0 + col] : 0.0;
-                okmask[h] = 0;
+                const double sb = cok ? g.exb[g.brow0 + col] : 0.0;
+                double cold[32];
+                unsigned okmask = 0;
 #pragma unroll
                 for (int r = 0; r < 32; r++) {
                     const int row = m0 + q * 32 + r;
                     const bool ok = row < g.M && cok && (!g.tri || ((int64_t)col + g.coff <= (int64_t)row + g.roff));
-                    okmask[h] |= ok ? (1u << r) : 0u;
-                    cold[h][r] = ok ? g.C[(int64_t)row * g.ldc + col] : 0.0;
+                    okmask |= ok ? (1u << r) : 0u;
+                    cold[r] = ok ? g.C[(int64_t)row * g.ldc + col] : 0.0;
                 }
-            }
-            mbar_wait(tfull, tile_it & 1);
-            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-#pragma unroll
-            for (int h = 0; h < 2; h++) {
-                double acc[32];
-#pragma unroll
-                for (int j = 0; j < 32; j++) acc[j] = 0.0;
-                double w = 1.0;
-#pragma unroll 1
-                for (int c = 0; c < OZ_S; c++) {
-                    uint32_t v[32];
-                    tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(c * OZ_BN + h * 32), v);
-#pragma unroll
-                    for (int j = 0; j < 32; j++) acc[j] = fma(i32_to_f64(v[j]), w, acc[j]);
-                    w *= (1.0 / 128.0);
-                }
-                if (h == 1) {
-                    // all TMEM reads of this warp are done: let the MMA warp start the next tile
-                    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-                    __syncwarp();
-                    if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(tempty) : "memory");
-                }
-#pragma unroll
-                for (int j = 0; j < 32; j++) tbuf[lane * 33 + j] = acc[j] * sa;
-                __syncwarp();
-                const int col = n0 + h * 32 + lane;
 #pragma unroll
                 for (int r = 0; r < 32; r++)
-                    if ((okmask[h] >> r) & 1u) g.C[(int64_t)(m0 + q * 32 + r) * g.ldc + col] = cold[h][r] + tbuf[r * 33 + lane] * sb[h];
+                    if ((okmask >> r) & 1u) g.C[(int64_t)(m0 + q * 32 + r) * g.ldc + col] = cold[r] + tbuf[r * 33 + lane] * sb;
                 __syncwarp();
             }
+            if (warp == 2) OZ_STAMP(7);
             tile_it++;
         }
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
-    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");   // no peer still targets this CTA
+    if (CS > 1) asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");   // no peer still targets this CTA
     if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
 }
 
@@ -742,7 +464,8 @@ int oz_gemm(Ctx* ctx, const void* bufA, int64_t rowsA_total, int64_t arow0, cons
             int64_t M, int64_t N, int64_t K, double alpha, double* C, int64_t ldc, int tri, int64_t roff, int64_t coff,
             cudaStream_t st, int tiles_per_cta) {
     if (M <= 0 || N <= 0) return 0;
-    if (K % OZ_BK != 0 || (arow0 & 127) || (brow0 & 63)) return BGP_E_ARG;
+    // K is bounded by the int32 accumulators: 7 digit pairs of at most 2^14 each per k
+    if (K % OZ_BK != 0 || K > OZ_MAX_K || (arow0 & 127) || (brow0 & 63)) return BGP_E_ARG;
     const int64_t rpa = oz_rows_pad(rowsA_total), rpb = oz_rows_pad(rowsB_total);
     OzArgs g;
     g.sa = reinterpret_cast<const int8_t*>(bufA); g.nrb_a = rpa / 128; g.arow0 = arow0;
@@ -751,61 +474,49 @@ int oz_gemm(Ctx* ctx, const void* bufA, int64_t rowsA_total, int64_t arow0, cons
     g.exb = reinterpret_cast<const double*>(g.sb + rpb * K * OZ_S);
     g.C = C; g.ldc = ldc; g.M = (int)M; g.N = (int)N; g.K = (int)K; g.alpha = alpha; g.tri = tri; g.roff = roff; g.coff = coff;
     g.debug_noload = (ctx->gemm_cfg == 7) ? 1 : 0;
+    g.group = ctx->oz_group > 0 ? ctx->oz_group : 8;
+    g.brb_max = g.nrb_b - 1;
+    g.dbg = ctx->oz_dbg; g.dbg_cap = ctx->oz_dbg_cap;
     const int tiles_m = (int)((M + OZ_BM - 1) / OZ_BM), tiles_n = (int)((N + OZ_BN - 1) / OZ_BN);
     const uint64_t bit = 1ull << (ctx->device & 63);
-    if (ctx->gemm_cfg == 6) {          // one tile per CTA (kept for comparison / debugging)
-        constexpr int SMEM = OZ_STAGES * (OZ_A_STAGE + OZ_B_STAGE) + 1024 + 256;
-        static thread_local uint64_t attr_done = 0;
-        if (!(attr_done & bit)) {
-            BGP_CUDA_OK(cudaFuncSetAttribute(oz_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
-            attr_done |= bit;
-        }
-        oz_mma_kernel<<<tiles_m * tiles_n, 192, SMEM, st>>>(g, tiles_m, tiles_n);
-    } else {
-        constexpr int SMEM = OZ_STAGES * (OZ_A_STAGE + OZ_B_STAGE) + 4 * OZ_TBUF * (int)sizeof(double) + 1024 + 256;
-        static thread_local uint64_t attr_done = 0;
-        static thread_local int sm_count[64] = {0};
-        if (!(attr_done & bit)) {
-            BGP_CUDA_OK(cudaFuncSetAttribute(oz_mma_persistent_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
-            BGP_CUDA_OK(cudaDeviceGetAttribute(&sm_count[ctx->device & 63], cudaDevAttrMultiProcessorCount, ctx->device));
-            attr_done |= bit;
-        }
-        // tiles per CTA: enough to amortise the prologue and pipeline across tiles, few enough that CTAs keep retiring so
-        // the high-priority panel stream of the look-ahead Cholesky still finds free SMs (a fully persistent grid would
-        // hold every SM until the whole update is done).  tiles_per_cta <= 0 -> fully persistent (one CTA per SM).
-        const int total = tiles_m * tiles_n;
-        const int nsm = sm_count[ctx->device & 63];
-        const int tpc = tiles_per_cta > 0 ? tiles_per_cta : 0;
-        const int cs = (tpc == 0) ? ctx->oz_cluster : 1;
-        if (cs == 2 || cs == 4) {
-            static thread_local uint64_t attr2_done = 0;
-            auto kern = (cs == 2) ? oz_mma_cluster_kernel<2> : oz_mma_cluster_kernel<4>;
-            if (!(attr2_done & bit)) {
-                BGP_CUDA_OK(cudaFuncSetAttribute(oz_mma_cluster_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
-                BGP_CUDA_OK(cudaFuncSetAttribute(oz_mma_cluster_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
-                attr2_done |= bit;
-            }
-            const int tiles_ng = (tiles_n + cs - 1) / cs;
-            const int total_g = tiles_m * tiles_ng;
-            int ncl = nsm / cs;
-            if (ncl > total_g) ncl = total_g;
-            cudaLaunchConfig_t cfg = {};
-            cfg.gridDim = dim3((unsigned)(ncl * cs));
-            cfg.blockDim = dim3(192);
-            cfg.dynamicSmemBytes = SMEM;
-            cfg.stream = st;
-            cudaLaunchAttribute at[1];
-            at[0].id = cudaLaunchAttributeClusterDimension;
-            at[0].val.clusterDim.x = cs; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
-            cfg.attrs = at; cfg.numAttrs = 1;
-            const int64_t brb_max = g.nrb_b - 1;
-            BGP_CUDA_OK(cudaLaunchKernelEx(&cfg, kern, g, tiles_m, tiles_n, brb_max));
-            ctx->launches++;
-            return 0;
-        }
-        const int grid = tpc > 0 ? (total + tpc - 1) / tpc : (total < nsm ? total : nsm);
-        oz_mma_persistent_kernel<<<grid, 192, SMEM, st>>>(g, tiles_m, tiles_n, tpc);
+    constexpr int SMEM = OZ_STAGES * (OZ_A_STAGE + OZ_B_STAGE) + 4 * OZ_TBUF * (int)sizeof(double) + 1024 + 256;
+    static thread_local uint64_t attr_done = 0;
+    static thread_local int sm_count[64] = {0};
+    if (!(attr_done & bit)) {
+        BGP_CUDA_OK(cudaFuncSetAttribute(oz_mma_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
+        BGP_CUDA_OK(cudaFuncSetAttribute(oz_mma_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
+        BGP_CUDA_OK(cudaFuncSetAttribute(oz_mma_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
+        BGP_CUDA_OK(cudaDeviceGetAttribute(&sm_count[ctx->device & 63], cudaDevAttrMultiProcessorCount, ctx->device));
+        attr_done |= bit;
     }
+    // tiles per CTA: enough to amortise the prologue and pipeline across tiles, few enough that CTAs keep retiring so
+    // the high-priority panel stream of the look-ahead Cholesky still finds free SMs (a fully persistent grid would
+    // hold every SM until the whole update is done).  tiles_per_cta <= 0 -> fully persistent (one CTA per SM).
+    const int nsm = sm_count[ctx->device & 63];
+    const int tpc = tiles_per_cta > 0 ? tiles_per_cta : 0;
+    const int cs = (tpc == 0) ? ctx->oz_cluster : 1;
+    if (cs == 2 || cs == 4) {
+        auto kern = (cs == 2) ? oz_mma_kernel<2> : oz_mma_kernel<4>;
+        const int tiles_ng = (tiles_n + cs - 1) / cs;
+        const int total_g = tiles_m * tiles_ng;
+        int ncl = nsm / cs;
+        if (ncl > total_g) ncl = total_g;
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3((unsigned)(ncl * cs));
+        cfg.blockDim = dim3(192);
+        cfg.dynamicSmemBytes = SMEM;
+        cfg.stream = st;
+        cudaLaunchAttribute at[1];
+        at[0].id = cudaLaunchAttributeClusterDimension;
+        at[0].val.clusterDim.x = cs; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+        cfg.attrs = at; cfg.numAttrs = 1;
+        BGP_CUDA_OK(cudaLaunchKernelEx(&cfg, kern, g, tiles_m, tiles_n, 0));
+        ctx->launches++;
+        return 0;
+    }
+    const int total = tiles_m * tiles_n;
+    const int grid = tpc > 0 ? (total + tpc - 1) / tpc : (total < nsm ? total : nsm);
+    oz_mma_kernel<1><<<grid, 192, SMEM, st>>>(g, tiles_m, tiles_n, tpc);
     BGP_LAUNCH_OK(ctx);
     return 0;
 }

@@ -5,13 +5,18 @@ A *step* is one full pass of the hot path over one synthetic 8s1p data set (SURV
     build K (Wiener + RBF-ARD + noise)  ->  Cholesky  ->  alpha  ->  LML  ->  predict mean/var at M=300 queries.
 N=1 GPU   : BASELINE.json configs[1]  (full_gp, N=40 000, D=3(+t), 1xB200).
 N>1 GPUs  : configs[3]  (one independent N=40 000 GP per GPU, no collective; weak scaling) -- the reference's own
-            process-per-GPU layout (gp_runner.py:246-298).  `--workload sharded` runs configs[4] instead (one GP
-            block-row-sharded over all ranks with NCCL panel broadcasts).
+            process-per-GPU layout (gp_runner.py:246-298) -- is the line's `value`; the SAME line carries a "sharded" object:
+            configs[4], ONE N=200 000 GP block-row-sharded over all ranks with NCCL panel exchanges (strong scaling), with its
+            seconds per step, per-phase split, NCCL bytes and parity numbers (oracle at n=5000, 1-GPU engine at N=40 000,
+            matrix-free residual at full size).  `--workload sharded` prints configs[4] as the primary line instead.
+--workload train : configs[2] (Matern-5/2 + Periodic, N=80 000, LML + analytic-gradient passes; a step = one pass).
 
 value  = algorithmic GFLOP/s (N^3/3 + N^2 M + 2 N^2 per GP) with X, y resident in HBM.
 e2e    = the same metric through the public API with HOST (pinned) inputs and host outputs inside the timed region.
---impl reference times the CPU restatement of the reference's GPyTorch Cholesky path (oracle/gp_oracle.py; GPyTorch
-itself is not installable here, DESIGN.md "Reference arm") on the box's host cores on a bounded sample.
+--impl reference times the reference's CPU path for the SAME config on the box's host cores: the torch fp64 restatement of
+what GPyTorch executes under max_cholesky_size(N+1) (oracle/torch_ref.py; BASELINE.md section 3 -- GPyTorch itself is not
+installable here, DESIGN.md "Reference arm").  One N=40 000 step costs ~1 min of CPU, so the arm runs as many of the
+requested steps as fit `--ref-budget-s` (at least one) and reports `steps_run`.
 """
 from __future__ import annotations
 
@@ -30,13 +35,44 @@ sys.path.insert(0, ROOT)
 M_QUERY = 300
 NOISE = 2.33e-6
 FP64_DMMA_PEAK_TFLOPS = 37.1   # measured on this pool's B200: profiles/fp64_peak_r01.txt (MEASURED_PEAKS.json has no fp64 entry)
-# dram__bytes_read.sum + dram__bytes_write.sum summed over the kernels of one bgp_potrf call, from the committed ncu launch
-# lists (profiles/launches_r01_final_summary.txt: int8 path 280 GB; launches_r01_summary.txt: DMMA-only path 315 GB) -- N -> bytes
-TRAFFIC_BYTES_PER_POTRF = {40000: 2.8e11}
+OZ_PAIRS = 28                  # int8 digit-plane products per fp64 product (csrc/ozaki.cu: 7 planes, pairs with s+t <= 6)
+METRIC = "exact_gp_fit_predict_gflops"
 
 
 def algorithmic_flops(n: int, m: int = M_QUERY) -> float:
     return n ** 3 / 3.0 + float(n) ** 2 * m + 2.0 * float(n) ** 2
+
+
+def train_pass_flops(n: int) -> float:
+    """LML + gradient pass: POTRF N^3/3 + POTRI 2N^3/3 + the O(N^2) sweeps."""
+    return float(n) ** 3 + 4.0 * float(n) ** 2
+
+
+def int8_peak() -> dict:
+    """tcgen05 kind::i8 peak measured on this pool (tools/microbench/i8_peak.cu -> profiles/i8_peak_r02.jsonl);
+    MEASURED_PEAKS.json records bf16 only.  Fallback: 2 x its bf16 figure, labelled as derived."""
+    try:
+        rows = [json.loads(l) for l in open(os.path.join(ROOT, "profiles", "i8_peak_r02.jsonl")) if l.strip().startswith("{")]
+        r = next(x for x in rows if x.get("mode") == "N256")
+        return {"sustained": float(r["sustained_TOPs"]), "burst": float(r["burst_TOPs"]),
+                "source": "profiles/i8_peak_r02.jsonl (tools/microbench/i8_peak.cu, M=128 N=256 K=32 tcgen05.mma kind::i8 "
+                          "back to back from shared memory; sustained = 1 s under the 1 kW cap, burst = best 2 ms)"}
+    except Exception:
+        try:
+            bf16 = float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["bf16_tflops"])
+            src = "DERIVED: 2 x MEASURED_PEAKS.json bf16_tflops (profiles/i8_peak_r02.jsonl missing)"
+        except Exception:
+            bf16, src = 1590.0, "DERIVED: 2 x fallback 1.59 PFLOP/s (B200_PROFILING.md)"
+        return {"sustained": 2.0 * bf16, "burst": 2.0 * bf16, "source": src}
+
+
+def ncu_traffic(kernel: str):
+    """dram bytes per launch of the dominant kernel from this round's committed `ncu --set full` capture (None when absent)."""
+    try:
+        d = json.load(open(os.path.join(ROOT, "profiles", "ncu_r02_traffic.json")))
+        return d.get(kernel)
+    except Exception:
+        return None
 
 
 def step_roofline(n: int, sec: float, world: int, ozaki: bool) -> dict:
@@ -45,14 +81,11 @@ def step_roofline(n: int, sec: float, world: int, ozaki: bool) -> dict:
     if not ozaki:
         return {"bound": "tensor", "achieved": fp64_equiv, "peak": FP64_DMMA_PEAK_TFLOPS, "unit": "TFLOP/s per GPU (whole step)",
                 "frac": fp64_equiv / FP64_DMMA_PEAK_TFLOPS, "traffic": None}
-    try:
-        bf16 = float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["bf16_tflops"])
-        src = "2 x MEASURED_PEAKS.json bf16_tflops"
-    except Exception:
-        bf16, src = 1590.0, "2 x fallback 1.59 PFLOP/s"
-    ach = 36.0 * fp64_equiv
-    return {"bound": "tensor", "achieved": ach, "peak": 2.0 * bf16, "unit": "TOP/s int8 per GPU (whole step; 36 int8 ops per fp64 flop)",
-            "frac": ach / (2.0 * bf16), "peak_source": src, "fp64_equivalent_tflops_per_gpu": fp64_equiv,
+    pk = int8_peak()
+    ach = OZ_PAIRS * fp64_equiv
+    return {"bound": "tensor", "achieved": ach, "peak": pk["sustained"],
+            "unit": f"TOP/s int8 per GPU (whole step; {OZ_PAIRS} int8 ops per fp64 flop)",
+            "frac": ach / pk["sustained"], "peak_source": pk["source"], "fp64_equivalent_tflops_per_gpu": fp64_equiv,
             "fp64_equivalent_over_dmma_peak": fp64_equiv / FP64_DMMA_PEAK_TFLOPS, "traffic": None}
 
 
@@ -108,45 +141,31 @@ class ClockSampler:
                 "reasons": sorted(reasons)}
 
 
-# ---------------------------------------------------------------------------------------------------- reference arm
-def run_reference(args, n_gpus: int):
-    """CPU arm: oracle port of the reference's GPyTorch Cholesky path on the host cores (rank 0 only)."""
-    rank = int(os.environ.get("RANK", "0"))
-    if rank != 0:
-        return
-    import numpy as np
-    from oracle import gp_oracle as orc
-    threads = _all_host_threads()
-    ns = args.ref_n
-    x, y = orc.synth_field_data(ns, seed=0)
-    xq = orc.query_grid(x)
-    spec = orc.battgp_spec()
-
-    def step():
-        f = orc.fit(spec, x, y, NOISE)
-        return orc.predict(spec, x, f, xq)
-
-    for _ in range(args.warmup if args.warmup < 2 else 1):   # CPU warm-up is about page faults only
-        step()
-    t0 = time.perf_counter()
-    for _ in range(args.steps):
-        step()
-    dt = (time.perf_counter() - t0) / args.steps
-    gf = algorithmic_flops(ns) / dt * 1e-9
-    sample = f"fit+predict at N={ns} (same generator/hyper-parameters as the N={args.n} workload), fp64 numpy/LAPACK"
-    line = {"impl": "reference", "metric": "exact_gp_fit_predict_gflops", "value": gf, "unit": "GF/s", "n_gpus": n_gpus,
-            "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": workload_name(args, n_gpus), "n": args.n, "m_query": M_QUERY, "kernel": "wiener+rbf_ard",
-                       "sample_n": ns},
-            "cpu_baseline": {"value": gf, "unit": "GF/s", "cores": threads, "kind": "port", "sample": sample},
-            "e2e": {"value": gf, "unit": "GF/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(line), flush=True)
+# ---------------------------------------------------------------------------------------------------- workload naming
+def workload_config(args, n_gpus: int) -> dict:
+    """The `config` object: what is computed, nothing measured -- identical in the b200 and the reference arm."""
+    n = args.n
+    if args.workload == "train":
+        return {"workload": f"full_gp Matern-5/2-ARD(I,SOC,T) + Periodic(t) N={n}, LML + analytic-gradient passes "
+                            f"(hyper-parameter optimisation step), 1xB200 (BASELINE configs[2])",
+                "n": n, "kernel": "matern52_ard+periodic", "l2_policy": "inputs_exceed_l2 (K and K^-1 are %.1f GB each, rebuilt every pass)" % (8.0 * n * n / 1e9)}
+    if args.workload == "sharded":
+        wl = f"full_gp Wiener+RBF-ARD N={n} block-row-sharded Cholesky over {n_gpus} GPU(s) (BASELINE configs[4])"
+    elif n_gpus == 1:
+        wl = f"full_gp Wiener+RBF-ARD N={n} D=3(+t) fit+predict on 1xB200 (BASELINE configs[1])"
+    else:
+        wl = f"8s1p per-cell batch: {n_gpus} independent full_gp N={n}, one per GPU, no collective (BASELINE configs[3])"
+    return {"workload": wl, "n": n, "m_query": M_QUERY, "kernel": "wiener+rbf_ard",
+            "l2_policy": "inputs_exceed_l2 (K is %.1f GB per GP, rebuilt every step)" % (8.0 * n * n / 1e9)}
 
 
 def _all_host_threads():
     """torchrun exports OMP_NUM_THREADS=1 for multi-rank launches; the CPU arm must still get every host core."""
     n = os.cpu_count() or 1
+    try:
+        n = min(n, len(os.sched_getaffinity(0)))
+    except Exception:
+        pass
     try:
         from threadpoolctl import threadpool_limits
         threadpool_limits(limits=n)
@@ -155,47 +174,106 @@ def _all_host_threads():
     try:
         import torch
         torch.set_num_threads(n)
-    except Exception:
-        pass
-    try:
-        from threadpoolctl import threadpool_info
-        return max([p.get("num_threads", 1) for p in threadpool_info()] or [1])
+        return int(torch.get_num_threads())
     except Exception:
         return n
 
 
-def workload_name(args, n_gpus):
-    if args.workload == "sharded":
-        return f"full_gp Wiener+RBF-ARD N={args.n} block-row-sharded Cholesky over {n_gpus} GPU(s) (BASELINE configs[4])"
-    if n_gpus == 1:
-        return f"full_gp Wiener+RBF-ARD N={args.n} D=3(+t) fit+predict on 1xB200 (BASELINE configs[1])"
-    return f"8s1p per-cell batch: {n_gpus} independent full_gp N={args.n}, one per GPU, no collective (BASELINE configs[3])"
+def _cpu_info() -> str:
+    try:
+        for ln in open("/proc/cpuinfo"):
+            if ln.startswith("model name"):
+                return ln.split(":", 1)[1].strip()
+    except Exception:
+        pass
+    return "unknown"
+
+
+# ---------------------------------------------------------------------------------------------------- reference arm
+def _cpu_reference_steps(n: int, max_steps: int, budget_s: float, warm: bool = True):
+    """Runs the torch fp64 reference path (oracle/torch_ref.py) at size n: returns (seconds per step, steps_run, phases)."""
+    from oracle import gp_oracle as orc
+    from oracle import torch_ref
+    if warm:                                    # thread pools / page faults only; untimed
+        xw, yw = orc.synth_field_data(min(n, 2000), seed=1)
+        torch_ref.fit_predict(xw, yw, orc.query_grid(xw), noise=NOISE)
+    x, y = orc.synth_field_data(n, seed=0)
+    xq = orc.query_grid(x)
+    times, phases = [], None
+    t_start = time.perf_counter()
+    while len(times) < max(1, max_steps):
+        t0 = time.perf_counter()
+        r = torch_ref.fit_predict(x, y, xq, noise=NOISE)
+        times.append(time.perf_counter() - t0)
+        phases = r["seconds"]
+        del r
+        if time.perf_counter() - t_start + times[-1] > budget_s:
+            break
+    return statistics.mean(times), len(times), phases
+
+
+def _cpu_train_pass(n: int):
+    """One LML + gradient pass of configs[2] through the numpy oracle (seconds)."""
+    from oracle import gp_oracle as orc
+    x, y = orc.synth_field_data(n, seed=0)
+    t0 = time.perf_counter()
+    orc.lml_grad(orc.matern_periodic_spec(), x, y, NOISE)
+    return time.perf_counter() - t0
+
+
+def run_reference(args, n_gpus: int):
+    """CPU arm (rank 0 only): the reference's path for the same config on the host cores."""
+    if int(os.environ.get("RANK", "0")) != 0:
+        return
+    threads = _all_host_threads()
+    cfg = workload_config(args, n_gpus)
+    if args.workload == "train":
+        ns = args.ref_n if args.ref_n > 0 else min(args.n, 6000)
+        dt_s = _cpu_train_pass(ns)
+        dt = dt_s * (args.n / ns) ** 3
+        gf = train_pass_flops(args.n) / dt * 1e-9
+        sample = (f"one LML+gradient pass of the numpy/LAPACK oracle at N={ns} ({dt_s:.1f} s), EXTRAPOLATED x (N/{ns})^3 to N={args.n} "
+                  f"(K and K^-1 at N={args.n} do not fit the time budget on CPU)")
+        steps_run, phases, kind = 1, None, "port"
+    else:
+        # every BASELINE config of this path is built from N=40 000 GPs except configs[4] (N=200 000: 320 GB, hours of CPU --
+        # BASELINE.md section 3: measure at 40k and label the rate as extrapolated)
+        ns = args.ref_n if args.ref_n > 0 else min(args.n, 40000)
+        dt_s, steps_run, phases = _cpu_reference_steps(ns, args.steps, args.ref_budget_s)
+        gf = algorithmic_flops(ns) / dt_s * 1e-9
+        dt = algorithmic_flops(args.n) / (gf * 1e9)
+        sample = (f"{steps_run} fit+predict step(s) at N={ns} (same generator/hyper-parameters), torch fp64 on {threads} threads: "
+                  f"vectorised build -> linalg.cholesky_ex -> cholesky_solve -> solve_triangular (M={M_QUERY})")
+        if ns != args.n:
+            sample += f"; GF/s is the measured N={ns} rate, ms_per_step EXTRAPOLATED to N={args.n} at that rate"
+        if n_gpus > 1:
+            sample += f"; one CPU job (the {n_gpus} GPs of the batch would run one after another at this rate)"
+        kind = "port"
+    line = {"impl": "reference", "metric": METRIC if args.workload != "train" else "exact_gp_lml_grad_pass_gflops",
+            "value": gf, "unit": "GF/s", "n_gpus": n_gpus,
+            "steps": args.steps, "warmup": args.warmup, "steps_run": steps_run, "ms_per_step": dt * 1e3, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": cfg,
+            "detail": {"sample_n": ns, "phase_seconds": phases, "cpu": _cpu_info(), "os_cpu_count": os.cpu_count(),
+                       "time_budget_s": args.ref_budget_s,
+                       "note": "steps_run of the requested steps were executed inside the time budget; ms_per_step is their mean"},
+            "cpu_baseline": {"value": gf, "unit": "GF/s", "cores": threads, "kind": kind, "sample": sample},
+            "e2e": {"value": gf, "unit": "GF/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+def cpu_baseline(args):
+    threads = _all_host_threads()
+    ns = args.ref_n if args.ref_n > 0 else min(args.n, 40000)
+    dt, steps_run, phases = _cpu_reference_steps(ns, 1, 0.0)
+    return {"value": algorithmic_flops(ns) / dt * 1e-9, "unit": "GF/s", "cores": threads, "kind": "port",
+            "sample": f"one fit+predict at N={ns} (same generator/hyper-parameters), {dt:.1f} s of torch fp64 "
+                      f"(build {phases['build']:.1f} s, cholesky_ex {phases['cholesky']:.1f} s, predict {phases['predict']:.1f} s) on {_cpu_info()}"}
 
 
 # ---------------------------------------------------------------------------------------------------- GPU arm
-def cpu_baseline(args):
-    import numpy as np  # noqa: F401
-    from oracle import gp_oracle as orc
-    threads = _all_host_threads()
-    ns = args.ref_n
-    x, y = orc.synth_field_data(ns, seed=0)
-    xq = orc.query_grid(x)
-    spec = orc.battgp_spec()
-    t0 = time.perf_counter()
-    f = orc.fit(spec, x, y, NOISE)
-    orc.predict(spec, x, f, xq)
-    dt = time.perf_counter() - t0
-    return {"value": algorithmic_flops(ns) / dt * 1e-9, "unit": "GF/s", "cores": threads, "kind": "port",
-            "sample": f"one fit+predict at N={ns} (same generator/hyper-parameters), {dt:.1f} s of fp64 numpy/LAPACK"}
-
-
-def run_gpu(args, n_gpus: int):
-    import numpy as np
+def _init_dist(n_gpus: int):
     import torch
     import torch.distributed as dist
-    from battgp_b200 import engine as E
-    from battgp_b200.synth import query_grid, synth_field_data
-
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -207,10 +285,26 @@ def run_gpu(args, n_gpus: int):
     dev = torch.device("cuda", local_rank)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
+    return rank, local_rank, world, dev
 
+
+def run_gpu(args, n_gpus: int):
+    import torch
+    import torch.distributed as dist
+    from battgp_b200 import engine as E
+    from battgp_b200.synth import query_grid, synth_field_data
+
+    rank, local_rank, world, dev = _init_dist(n_gpus)
     if args.workload == "sharded":
         from battgp_b200 import sharded
-        return sharded.bench(args, rank, world, dev)
+        line = sharded.bench(args, rank, world, dev)
+        if rank == 0:
+            print(json.dumps(line), flush=True)
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    if args.workload == "train":
+        return run_train(args, rank, world, dev)
 
     eng = E.get_engine(dev)
     n = args.n
@@ -265,7 +359,9 @@ def run_gpu(args, n_gpus: int):
     if rank == 0:
         sampler.start()
     l0 = eng.launches
+    eng.kernel_profile(True)                      # CUDA events around every trailing-update launch (bgp_ctx_oz_profile)
     ms_total = timed(step_device, args.steps, collect_potrf=True)
+    kprof = eng.kernel_profile(False)
     launches = eng.launches - l0
     clocks = sampler.stop() if rank == 0 else None
     # e2e: host buffers in, host results out
@@ -283,45 +379,53 @@ def run_gpu(args, n_gpus: int):
     sec_e2e = ms_e2e / 1e3 / args.steps
     value = world * flops / sec * 1e-9
     e2e_value = world * flops / sec_e2e * 1e-9
+
+    sharded_obj = None
+    if world > 1 and not args.no_sharded:
+        # configs[4] in the same run: free this rank's per-GPU buffers first (N=200k on 2 GPUs needs 80 GB per rank)
+        del K, xd, yd, xqd
+        eng.release_workspace()
+        torch.cuda.empty_cache()
+        from battgp_b200 import sharded
+        sharded_obj = sharded.bench_object(args, rank, world, dev)
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
         return
     pm = statistics.mean(potrf_ms)
     fp64_equiv = n ** 3 / 3.0 / (pm * 1e-3) * 1e-12
-    peaks = {}
-    try:
-        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
-    except Exception:
-        pass
-    bf16_peak = float(peaks.get("bf16_tflops", 1590.0))
-    bf16_src = "MEASURED_PEAKS.json bf16_tflops (burst)" if "bf16_tflops" in peaks else "fallback 1.59 PFLOP/s (B200_PROFILING.md)"
     if eng.ozaki:
-        # the trailing updates run as 36 exact int8 x int8 -> int32 tcgen05 products per fp64 product (csrc/ozaki.cu);
-        # the int8 tensor rate on sm_100a is 2x the bf16 rate, so the denominator is 2 x the measured bf16 peak
-        int8_ops = 36.0 * n ** 3 / 3.0
-        achieved = int8_ops / (pm * 1e-3) * 1e-12
-        peak = 2.0 * bf16_peak
-        roof = {"bound": "tensor", "kernel": "bgp_potrf_aug: oz_mma_persistent_kernel (tcgen05.mma kind::i8 / UTCIMMA, TMEM accumulators, cp.async.bulk "
-                                             "pipeline) trailing updates incl. the M query rows + DMMA panel/leaf kernels",
-                "achieved": achieved, "peak": peak, "unit": "TOP/s (int8, 36 int8 ops per fp64 flop of the Ozaki scheme)",
-                "frac": achieved / peak, "peak_source": "2 x " + bf16_src + " (no int8 entry; kind::i8 issues at twice the kind::f16 rate)",
-                "fp64_equivalent_tflops": fp64_equiv, "fp64_dmma_peak_tflops": FP64_DMMA_PEAK_TFLOPS,
-                "fp64_equivalent_over_dmma_peak": fp64_equiv / FP64_DMMA_PEAK_TFLOPS,
-                "algorithmic_flop_per_launch": n ** 3 / 3.0, "traffic": TRAFFIC_BYTES_PER_POTRF.get(n)}
+        # dominant kernel: the int8/tcgen05 trailing updates (csrc/ozaki.cu oz_mma_kernel), timed live with CUDA events on the
+        # stream they are launched on, inside the timed steps; algorithmic flop = 2 x (tile area actually computed) x K
+        pk = int8_peak()
+        k_ms, k_flop, k_n = kprof["ms"], kprof["flop"], kprof["launches"]
+        k_fp64 = k_flop / (k_ms * 1e-3) * 1e-12 if k_ms > 0 else 0.0
+        achieved = OZ_PAIRS * k_fp64
+        roof = {"bound": "tensor",
+                "kernel": "oz_mma_kernel (csrc/ozaki.cu): trailing updates A22 -= L21 L21^T as 28 exact int8 digit-plane products per "
+                          "fp64 product on tcgen05.mma kind::i8 (UTCIMMA), accumulators in TMEM, cp.async.bulk operand pipeline",
+                "achieved": achieved, "peak": pk["sustained"], "unit": f"TOP/s (int8; {OZ_PAIRS} int8 ops per fp64 flop)",
+                "frac": achieved / pk["sustained"], "peak_source": pk["source"], "peak_burst": pk["burst"],
+                "frac_of_burst_peak": achieved / pk["burst"],
+                "launches_timed": k_n, "avg_launch_ms": k_ms / max(k_n, 1),
+                "algorithmic_flop_per_launch": k_flop / max(k_n, 1), "kernel_fp64_equivalent_tflops": k_fp64,
+                "kernel_share_of_step": (k_ms / args.steps) / (sec * 1e3),
+                "note": "launch durations are CUDA-event times on the launching stream while the look-ahead panel stream shares the SMs",
+                "potrf": {"ms": pm, "fp64_equivalent_tflops": fp64_equiv, "fp64_dmma_peak_tflops": FP64_DMMA_PEAK_TFLOPS,
+                          "fp64_equivalent_over_dmma_peak": fp64_equiv / FP64_DMMA_PEAK_TFLOPS,
+                          "int8_tops": OZ_PAIRS * fp64_equiv, "frac_of_int8_peak": OZ_PAIRS * fp64_equiv / pk["sustained"]},
+                "traffic": ncu_traffic("oz_mma_kernel")}
     else:
         roof = {"bound": "tensor", "kernel": "bgp_potrf (gemm_nt_kernel DMMA.8x8x4 trailing updates + leaf/panel kernels)",
                 "achieved": fp64_equiv, "peak": FP64_DMMA_PEAK_TFLOPS, "unit": "TFLOP/s", "frac": fp64_equiv / FP64_DMMA_PEAK_TFLOPS,
                 "peak_source": "measured FP64 DMMA microbenchmark on this pool (profiles/fp64_peak_r01.txt); "
                                "MEASURED_PEAKS.json records no fp64 peak (tcgen05 has no f64 kind)",
-                "algorithmic_flop_per_launch": n ** 3 / 3.0, "traffic": TRAFFIC_BYTES_PER_POTRF.get(n)}
+                "algorithmic_flop_per_launch": n ** 3 / 3.0, "traffic": None}
     line = {
-        "metric": "exact_gp_fit_predict_gflops", "value": value, "unit": "GF/s", "n_gpus": world, "steps": args.steps,
+        "metric": METRIC, "value": value, "unit": "GF/s", "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": "f64", "data": "synthetic",
-        "config": {"workload": workload_name(args, world), "n": n, "m_query": M_QUERY, "kernel": "wiener+rbf_ard",
-                   "l2_policy": "inputs_exceed_l2 (K is %.1f GB per GPU, rebuilt every step)" % (8.0 * n * n / 1e9),
-                   "fit_predict_seconds": sec, "potrf_ms": pm, "trailing_update_path": "int8_tcgen05_ozaki" if eng.ozaki else "fp64_dmma",
+        "dtype": "f64", "data": "synthetic", "config": workload_config(args, world),
+        "detail": {"fit_predict_seconds": sec, "potrf_ms": pm, "trailing_update_path": "int8_tcgen05_ozaki_7x8bit" if eng.ozaki else "fp64_dmma",
                    "residual_Kalpha_minus_y_over_y": resid, "lml": lml_chk, "predictions_finite_and_positive": finite},
         "clocks": clocks,
         "e2e": {"value": e2e_value, "unit": "GF/s", "seconds": sec_e2e,
@@ -329,11 +433,119 @@ def run_gpu(args, n_gpus: int):
         "gpu_launches": int(launches),
         "roofline": roof,
     }
+    if sharded_obj is not None:
+        line["sharded"] = sharded_obj
     if world == 1 and not args.no_cpu_baseline:
         line["cpu_baseline"] = cpu_baseline(args)
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
+
+
+def run_train(args, rank: int, world: int, dev):
+    """BASELINE configs[2]: Matern-5/2-ARD + Periodic, LML + analytic gradient passes at N (default 80 000) on one GPU.
+    A step = build K -> Cholesky -> alpha -> LML -> K^-1 (POTRI) -> fused gradient reduction (6+ hyper-parameters)."""
+    import numpy as np
+    import torch
+    from battgp_b200 import engine as E
+    from battgp_b200.synth import synth_field_data
+    if world != 1:
+        raise SystemExit("--workload train runs on one GPU")
+    eng = E.get_engine(dev)
+    n = args.n
+    spec = E.matern_periodic_spec()
+    x_np, y_np = synth_field_data(n, seed=0)
+    xd, yd = torch.tensor(x_np, device=dev), torch.tensor(y_np, device=dev)
+    xh, yh = torch.tensor(x_np).pin_memory(), torch.tensor(y_np).pin_memory()
+    K = E.alloc_matrix(n, n, dev)
+    W = E.alloc_matrix(n, n, dev)
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
+    phase = {"fit": [], "potri": [], "grad": []}
+
+    def one_pass(x, y, timed_phases=False):
+        if timed_phases:
+            ev[0].record()
+        st = E.fit(spec, x, y, NOISE, K_out=K)
+        if timed_phases:
+            ev[1].record()
+        eng.potri(st.L, st.dinv, W)
+        if timed_phases:
+            ev[2].record()
+        g = eng.lml_grad(spec, NOISE, x, st.L, st.alpha)
+        if timed_phases:
+            ev[3].record()
+            torch.cuda.synchronize(dev)
+            phase["fit"].append(ev[0].elapsed_time(ev[1])); phase["potri"].append(ev[1].elapsed_time(ev[2]))
+            phase["grad"].append(ev[2].elapsed_time(ev[3]))
+        return st.lml, g
+
+    def timed(fn, steps):
+        torch.cuda.synchronize(dev)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        torch.cuda.synchronize(dev)
+        return e0.elapsed_time(e1)
+
+    for _ in range(args.warmup):
+        one_pass(xd, yd)
+    sampler = ClockSampler(dev.index)
+    sampler.start()
+    l0 = eng.launches
+    ms_total = timed(lambda: one_pass(xd, yd, True), args.steps)
+    launches = eng.launches - l0
+    clocks = sampler.stop()
+
+    def pass_e2e():
+        lml, g = one_pass(xh.to(dev, non_blocking=True), yh.to(dev, non_blocking=True))
+        return lml, g.cpu()
+    pass_e2e()
+    ms_e2e = timed(pass_e2e, args.steps)
+    lml_full, g_full = one_pass(xd, yd)
+    # parity of loss and gradient against the oracle at n=1500 in the same run (checker only)
+    from oracle import gp_oracle as orc
+    nchk = 1500
+    xc, yc = synth_field_data(nchk, seed=5)
+    st = E.fit(spec, torch.tensor(xc, device=dev), torch.tensor(yc, device=dev), NOISE)
+    eng.potri(st.L, st.dinv)
+    gc = eng.lml_grad(spec, NOISE, st.x, st.L, st.alpha).cpu().numpy()
+    ref = orc.lml_grad(orc.matern_periodic_spec(), xc, yc, NOISE)
+    gref = [ref["noise"]]
+    for t in ref["terms"]:
+        gref += [t["outputscale"], *t["lengthscale"], *t["period"]]
+    gref = np.asarray(gref)
+    par = {"n": nchk, "lml_rel_err": abs(st.lml - ref["lml"]) / abs(ref["lml"]),
+           "grad_max_rel_err": float(np.max(np.abs(gc - gref) / np.maximum(np.abs(gref), 1e-300))),
+           "tolerance": {"lml_rel": 1e-9, "grad_rel": 1e-6}, "checker": "oracle/gp_oracle.py lml_grad (parity unpinned by the reference)"}
+    par["ok"] = bool(par["lml_rel_err"] < 1e-9 and par["grad_max_rel_err"] < 1e-6)
+    sec = ms_total / 1e3 / args.steps
+    sec_e2e = ms_e2e / 1e3 / args.steps
+    potri_s = statistics.mean(phase["potri"]) * 1e-3
+    potri_tf = (2.0 / 3.0) * n ** 3 / potri_s * 1e-12
+    pk = int8_peak()
+    line = {"metric": "exact_gp_lml_grad_pass_gflops", "value": train_pass_flops(n) / sec * 1e-9, "unit": "GF/s", "n_gpus": 1,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": workload_config(args, 1),
+            "detail": {"seconds_per_pass": sec, "phase_ms": {k: statistics.mean(v) for k, v in phase.items()}, "lml": lml_full,
+                       "grad": [float(v) for v in g_full.cpu()], "parity": par,
+                       "peak_mem_GB": torch.cuda.max_memory_allocated(dev) / 1e9},
+            "clocks": clocks,
+            "e2e": {"value": train_pass_flops(n) / sec_e2e * 1e-9, "unit": "GF/s", "seconds": sec_e2e,
+                    "h2d_bytes_per_step": int(xh.numel() + yh.numel()) * 8, "d2h_bytes_per_step": int(g_full.numel()) * 8 + 8},
+            "gpu_launches": int(launches),
+            "roofline": {"bound": "tensor", "kernel": "bgp_potri (K^-1 = L^-T L^-1: trtri + lauum products on the int8/tcgen05 path, K-chunked)",
+                         "achieved": OZ_PAIRS * potri_tf, "peak": pk["sustained"], "unit": f"TOP/s (int8; {OZ_PAIRS} int8 ops per fp64 flop)",
+                         "frac": OZ_PAIRS * potri_tf / pk["sustained"], "peak_source": pk["source"],
+                         "algorithmic_flop_per_launch": (2.0 / 3.0) * n ** 3, "fp64_equivalent_tflops": potri_tf,
+                         "fp64_equivalent_over_dmma_peak": potri_tf / FP64_DMMA_PEAK_TFLOPS, "traffic": None}}
+    if not args.no_cpu_baseline:
+        ns = args.ref_n if args.ref_n > 0 else 4000
+        dt = _cpu_train_pass(ns)
+        line["cpu_baseline"] = {"value": train_pass_flops(ns) / dt * 1e-9, "unit": "GF/s", "cores": _all_host_threads(), "kind": "port",
+                                "sample": f"one LML+gradient pass of the numpy/LAPACK oracle at N={ns}: {dt:.1f} s"}
+    print(json.dumps(line), flush=True)
 
 
 def main():
@@ -342,14 +554,20 @@ def main():
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--size", dest="n", type=int, default=40000, help="training points per GP")
-    ap.add_argument("--workload", default="per_gpu", choices=["per_gpu", "sharded"])
-    ap.add_argument("--ref-n", type=int, default=10000, help="sample size of the CPU arm / cpu_baseline")
+    ap.add_argument("--size", dest="n", type=int, default=0, help="training points per GP (default 40000; sharded 200000; train 80000)")
+    ap.add_argument("--workload", default="per_gpu", choices=["per_gpu", "sharded", "train"])
+    ap.add_argument("--ref-n", type=int, default=0, help="size the CPU arm / cpu_baseline really runs (0 = the workload's, capped at 40000)")
+    ap.add_argument("--ref-budget-s", type=float, default=240.0, help="CPU arm: stop starting new steps after this many seconds")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-sharded", action="store_true", help="N>1: skip the configs[4] object")
+    ap.add_argument("--sharded-n", type=int, default=200000, help="N>1: size of the sharded GP in the 'sharded' object")
+    ap.add_argument("--sharded-steps", type=int, default=2)
     ap.add_argument("--verify", action="store_true", help="sharded workload: also report the matrix-free residual |K alpha - y|/|y|")
     ap.add_argument("--phases", action="store_true", help="sharded workload: extra synchronised pass reporting seconds per phase")
     ap.add_argument("--nb", type=int, default=1024, help="stripe height of the sharded workload")
     args = ap.parse_args()
+    if args.n <= 0:
+        args.n = {"per_gpu": 40000, "sharded": 200000, "train": 80000}[args.workload]
     if args.impl == "reference":
         run_reference(args, args.gpus)
     else:
