@@ -48,6 +48,8 @@ SIGNATURES = {
     "bgp_potrf_workspace_bytes": (_I64, [_P, _I64]),
     "bgp_ctx_set_workspace": (C.c_int, [_P, _P, _I64]),
     "bgp_ctx_launches": (_I64, [_P]),
+    "bgp_ctx_kernel_profile": (C.c_int, [_P, C.c_int]),
+    "bgp_ctx_kernel_profile_read": (C.c_int, [_P, C.POINTER(_D), C.POINTER(_D), C.POINTER(_I64)]),
     "bgp_cov_build": (C.c_int, [_P, _SPEC, _P, _I64, _I64, _P, _I64, _I64, _P, _I64, C.c_int, _P]),
     "bgp_cov_diag": (C.c_int, [_P, _SPEC, _P, _I64, _I64, _P, _P]),
     "bgp_gemm_nt": (C.c_int, [_P, _I64, _I64, _I64, _D, _P, _I64, _P, _I64, _D, _P, _I64, C.c_int, _I64, _I64, _P]),

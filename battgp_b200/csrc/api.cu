@@ -186,8 +186,25 @@ static int potrf_driver(Ctx* ctx, double* A, int64_t n, int64_t mx, int64_t lda,
             BGP_CUDA_OK(cudaStreamWaitEvent(mainst, ctx->ev_panel[k % 2], 0));
             mark(mainst);
             if (oz) {
+                const bool prof = ctx->prof != 0;
+                if (prof) {
+                    if (ctx->prof_ev.size() < 2 * (ctx->prof_used + 1)) {
+                        cudaEvent_t a, b;
+                        BGP_CUDA_OK(cudaEventCreate(&a));
+                        BGP_CUDA_OK(cudaEventCreate(&b));
+                        ctx->prof_ev.push_back(a); ctx->prof_ev.push_back(b);
+                        ctx->prof_flop.push_back(0.0);
+                    }
+                    BGP_CUDA_OK(cudaEventRecord(ctx->prof_ev[2 * ctx->prof_used], mainst));
+                }
                 if ((rc = oz_gemm(ctx, ozbuf[k & 1], below, wnext, ozbuf[k & 1], below, wnext, R - t0, n - t0, nbk, -1.0,
                                   A + t0 * lda + t0, lda, 1, 0, 0, mainst, ctx->oz_tpc))) return rc;
+                if (prof) {
+                    BGP_CUDA_OK(cudaEventRecord(ctx->prof_ev[2 * ctx->prof_used + 1], mainst));
+                    const double c = (double)(n - t0);          // lower triangle of the square part + the full extra rows
+                    ctx->prof_flop[ctx->prof_used] = 2.0 * (c * (c + 1.0) * 0.5 + (double)(R - n) * c) * (double)nbk;
+                    ctx->prof_used++;
+                }
             } else {
                 const double* Lt = A + t0 * lda + k0;
                 GemmArgs g{Lt, lda, Lt, lda, A + t0 * lda + t0, lda, (int)(R - t0), (int)(n - t0), (int)nbk, -1.0, 1.0, 1, 0, 0};
@@ -286,6 +303,7 @@ void bgp_ctx_destroy(bgp_ctx* p) {
     if (c->d_info) cudaFree(c->d_info);
     if (c->d_scal) cudaFree(c->d_scal);
     if (c->d_scratch) cudaFree(c->d_scratch);
+    for (auto& e : c->prof_ev) cudaEventDestroy(e);
     delete c;
 }
 
@@ -312,6 +330,7 @@ int bgp_ctx_set(bgp_ctx* p, const char* key, int value) {
     if (!strcmp(key, "ozaki")) { c->ozaki = value ? 1 : 0; return 0; }
     if (!strcmp(key, "oz_cluster")) { if (value != 1 && value != 2 && value != 4) return BGP_E_ARG; c->oz_cluster = value; return 0; }
     if (!strcmp(key, "oz_group")) { if (value < 1 || value > 1024) return BGP_E_ARG; c->oz_group = value; return 0; }
+    if (!strcmp(key, "oz_tpc_gemm")) { if (value < 0 || value > 4096) return BGP_E_ARG; c->oz_tpc_gemm = value; return 0; }
     if (!strcmp(key, "oz_tpc")) { if (value < 0 || value > 4096) return BGP_E_ARG; c->oz_tpc = value; return 0; }
     if (!strcmp(key, "gemm_cfg")) { if (value < 0 || value > 7) return BGP_E_ARG; c->gemm_cfg = value; return 0; }
     return BGP_E_ARG;
@@ -348,6 +367,31 @@ int bgp_ctx_set_workspace(bgp_ctx* p, void* ptr, int64_t bytes) {
 }
 
 int64_t bgp_ctx_launches(const bgp_ctx* p) { return p ? reinterpret_cast<const Ctx*>(p)->launches : 0; }
+
+int bgp_ctx_kernel_profile(bgp_ctx* p, int enable) {
+    if (!p) return BGP_E_ARG;
+    Ctx* c = reinterpret_cast<Ctx*>(p);
+    c->prof = enable ? 1 : 0;
+    c->prof_used = 0;
+    return 0;
+}
+
+int bgp_ctx_kernel_profile_read(bgp_ctx* p, double* ms, double* flop, int64_t* nlaunch) {
+    CTX_OR_FAIL(p);
+    double tms = 0.0, tfl = 0.0;
+    for (size_t i = 0; i < ctx->prof_used; i++) {
+        BGP_CUDA_OK(cudaEventSynchronize(ctx->prof_ev[2 * i + 1]));
+        float e = 0.f;
+        BGP_CUDA_OK(cudaEventElapsedTime(&e, ctx->prof_ev[2 * i], ctx->prof_ev[2 * i + 1]));
+        tms += e;
+        tfl += ctx->prof_flop[i];
+    }
+    if (ms) *ms = tms;
+    if (flop) *flop = tfl;
+    if (nlaunch) *nlaunch = (int64_t)ctx->prof_used;
+    ctx->prof_used = 0;
+    return 0;
+}
 
 int bgp_cov_build(bgp_ctx* c, const bgp_kernel_spec* spec, const double* X1, int64_t n1, int64_t ldx1, const double* X2,
                   int64_t n2, int64_t ldx2, double* out, int64_t ldo, int symmetric, void* stream) {
@@ -514,9 +558,10 @@ int bgp_oz_gemm(bgp_ctx* c, const void* bufA, int64_t rowsA, int64_t arow0, cons
     CTX_OR_FAIL(c);
     if (M < 0 || N < 0 || M > INT_MAX || N > INT_MAX) return BGP_E_ARG;
     if (M == 0 || N == 0) return 0;
-    if (!bufA || !bufB || !C || K <= 0 || K % 64 || ldc < N || arow0 < 0 || brow0 < 0 || arow0 + M > ((rowsA + 127) / 128) * 128 ||
+    if (!bufA || !bufB || !C || K <= 0 || K % 64 || K > 16384 || ldc < N || arow0 < 0 || brow0 < 0 || arow0 + M > ((rowsA + 127) / 128) * 128 ||
         brow0 + N > ((rowsB + 127) / 128) * 128) return BGP_E_ARG;
-    return oz_gemm(ctx, bufA, rowsA, arow0, bufB, rowsB, brow0, M, N, K, alpha, C, ldc, tri ? 1 : 0, roff, coff, (cudaStream_t)stream);
+    return oz_gemm(ctx, bufA, rowsA, arow0, bufB, rowsB, brow0, M, N, K, alpha, C, ldc, tri ? 1 : 0, roff, coff, (cudaStream_t)stream,
+                   ctx->oz_tpc_gemm);
 }
 
 int64_t bgp_gemm_nt_i8_work_bytes(int64_t M, int64_t N, int64_t K) {
@@ -527,7 +572,8 @@ int bgp_gemm_nt_i8(bgp_ctx* c, int64_t M, int64_t N, int64_t K, double alpha, co
                    int64_t ldb, double* C, int64_t ldc, int tri, int64_t roff, int64_t coff, void* work, int64_t work_bytes,
                    void* stream) {
     CTX_OR_FAIL(c);
-    if (M < 0 || N < 0 || K <= 0 || K % 64 || M > INT_MAX || N > INT_MAX) return BGP_E_ARG;
+    // K <= 16384: the int32 accumulators hold 7 digit pairs of at most 2^14 per k (csrc/ozaki.cu OZ_MAX_K)
+    if (M < 0 || N < 0 || K <= 0 || K % 64 || K > 16384 || M > INT_MAX || N > INT_MAX) return BGP_E_ARG;
     if (M == 0 || N == 0) return 0;
     if (!A || !B || !C || !work || lda < K || ldb < K || ldc < N || work_bytes < bgp_gemm_nt_i8_work_bytes(M, N, K)) return BGP_E_ARG;
     if ((uintptr_t)work & 255) return BGP_E_ARG;

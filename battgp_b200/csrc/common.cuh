@@ -3,6 +3,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <vector>
 #include "../../include/battgp_b200.h"
 
 namespace bgp {
@@ -30,18 +31,24 @@ struct Ctx {
     int sched_t4096 = 0;                    // int8 path only: 4096-wide panels from here up (0 = never)
     int sched_w0 = 0;                       // cap on the width of the first panel (its chain has nothing to hide behind)
     int sched_w1 = 0;                       // cap on the width of the second panel
-    int oz_cluster = 2;                     // CTAs per cluster sharing the A operand by multicast (1, 2 or 4) when fully persistent
+    int oz_cluster = 1;                     // CTAs per cluster sharing the A operand by multicast (1, 2 or 4) when fully persistent
     int oz_tpc = 2;                         // tiles per CTA of the int8 kernel inside bgp_potrf (0 = fully persistent)
     int ozaki = 0;                          // 1: big trailing updates of bgp_potrf go through the int8/tcgen05 path
     void* ws = nullptr;                     // caller-provided scratch (bgp_ctx_set_workspace)
     int64_t ws_bytes = 0;
     void* ws_trsm = nullptr;                // tail of ws used by the TRSM updates (set by bgp_potrf for its panels)
     int64_t ws_trsm_bytes = 0;
+    int oz_tpc_gemm = 0;                    // tiles per CTA of stand-alone bgp_oz_gemm calls (0 = fully persistent)
     int oz_group = 8;                       // tile rows per raster group of the int8 kernel
     long long* oz_dbg = nullptr;            // diagnostics: clock64 timeline of CTA 0 (bgp_debug_oz_timeline)
     int oz_dbg_cap = 0;
     int gemm_cfg = 0;                       // 0 = default big-tile config, else forced variant (probing)
     int64_t launches = 0;
+    // bgp_ctx_kernel_profile: timed CUDA events around every trailing-update launch of bgp_potrf (bench.py's roofline)
+    int prof = 0;
+    std::vector<cudaEvent_t> prof_ev;       // pairs (start, stop), re-used across calls
+    std::vector<double> prof_flop;          // algorithmic flop of launch i
+    size_t prof_used = 0;                   // launches recorded since the last read
 };
 
 void set_error(const char* what, cudaError_t e);

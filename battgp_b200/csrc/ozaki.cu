@@ -409,6 +409,11 @@ __global__ void __launch_bounds__(192, 1) oz_mma_kernel(OzArgs g, int tiles_m, i
             __syncwarp();
             if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(tempty) : "memory");
             if (warp == 2) OZ_STAMP(6);
+            // rows of this warp's 32-row block that exist and (tri) lie on or below the diagonal for a given column: [r_lo, 32)
+            // clipped to r_hi -- two small integers instead of a 64-bit predicate per element (the epilogue warp is alone on
+            // its scheduler, so its instruction count is what the store phase costs)
+            const int rbase = m0 + q * 32;
+            const int r_hi = min(32, g.M - rbase);
 #pragma unroll
             for (int h = 0; h < 2; h++) {
                 // TMEM hands a thread one ROW (lane), global memory wants a warp on one row segment: transpose through smem
@@ -419,18 +424,26 @@ __global__ void __launch_bounds__(192, 1) oz_mma_kernel(OzArgs g, int tiles_m, i
                 const int col = n0 + h * 32 + lane;
                 const bool cok = col < g.N;
                 const double sb = cok ? g.exb[g.brow0 + col] : 0.0;
-                double cold[32];
-                unsigned okmask = 0;
-#pragma unroll
-                for (int r = 0; r < 32; r++) {
-                    const int row = m0 + q * 32 + r;
-                    const bool ok = row < g.M && cok && (!g.tri || ((int64_t)col + g.coff <= (int64_t)row + g.roff));
-                    okmask |= ok ? (1u << r) : 0u;
-                    cold[r] = ok ? g.C[(int64_t)row * g.ldc + col] : 0.0;
+                int r_lo = 0;
+                if (g.tri) {
+                    const int64_t rmin = (int64_t)col + g.coff - g.roff - rbase;      // first row with col + coff <= row + roff
+                    r_lo = rmin > 32 ? 32 : (rmin < 0 ? 0 : (int)rmin);
                 }
+                const int r_end = cok ? r_hi : 0;
+                double* cp = g.C + (int64_t)rbase * g.ldc + col;
+                double cold[32];
+                if (__all_sync(0xffffffffu, r_lo == 0 && r_end == 32)) {                // interior tile: no predicates at all
 #pragma unroll
-                for (int r = 0; r < 32; r++)
-                    if ((okmask >> r) & 1u) g.C[(int64_t)(m0 + q * 32 + r) * g.ldc + col] = cold[r] + tbuf[r * 33 + lane] * sb;
+                    for (int r = 0; r < 32; r++) cold[r] = cp[(int64_t)r * g.ldc];
+#pragma unroll
+                    for (int r = 0; r < 32; r++) cp[(int64_t)r * g.ldc] = cold[r] + tbuf[r * 33 + lane] * sb;
+                } else {
+#pragma unroll
+                    for (int r = 0; r < 32; r++) cold[r] = (r >= r_lo && r < r_end) ? cp[(int64_t)r * g.ldc] : 0.0;
+#pragma unroll
+                    for (int r = 0; r < 32; r++)
+                        if (r >= r_lo && r < r_end) cp[(int64_t)r * g.ldc] = cold[r] + tbuf[r * 33 + lane] * sb;
+                }
                 __syncwarp();
             }
             if (warp == 2) OZ_STAMP(7);

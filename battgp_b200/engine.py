@@ -178,6 +178,17 @@ class Engine:
         _lib.check(self.L.bgp_ctx_set_workspace(self.h, C.c_void_p(0), 0), "bgp_ctx_set_workspace")
         self._ws = None
 
+    def kernel_profile(self, enable: bool):
+        """Timed CUDA events around the trailing-update launches of bgp_potrf (bench.py's roofline).  Turning it off
+        returns {"ms", "flop", "launches"} summed over the launches recorded since it was turned on."""
+        if enable:
+            _lib.check(self.L.bgp_ctx_kernel_profile(self.h, 1), "bgp_ctx_kernel_profile")
+            return None
+        ms, fl, nl = C.c_double(0.0), C.c_double(0.0), C.c_int64(0)
+        _lib.check(self.L.bgp_ctx_kernel_profile_read(self.h, C.byref(ms), C.byref(fl), C.byref(nl)), "bgp_ctx_kernel_profile_read")
+        _lib.check(self.L.bgp_ctx_kernel_profile(self.h, 0), "bgp_ctx_kernel_profile")
+        return {"ms": ms.value, "flop": fl.value, "launches": int(nl.value)}
+
     @property
     def launches(self) -> int:
         return int(self.L.bgp_ctx_launches(self.h))
@@ -258,8 +269,13 @@ class Engine:
                                               self._stream()), "bgp_oz_slice_gather")
         return buf
 
-    def oz_gemm(self, bufA, rowsA, arow0, bufB, rowsB, brow0, C_, K, alpha=-1.0, tri=False, roff=0, coff=0):
+    def oz_gemm(self, bufA, rowsA, arow0, bufB, rowsB, brow0, C_, K, alpha=-1.0, tri=False, roff=0, coff=0, tpc=0):
+        """``tpc`` tiles per CTA (0 = one persistent CTA per SM; > 0 lets CTAs retire so that a concurrent high-priority
+        stream finds free SMs -- the sharded look-ahead)."""
         M, N = C_.shape
+        if tpc != getattr(self, "_oz_tpc_gemm", 0):
+            self.set("oz_tpc_gemm", tpc)
+            self._oz_tpc_gemm = tpc
         rc = self.L.bgp_oz_gemm(self.h, _ptr(bufA), rowsA, arow0, _ptr(bufB), rowsB, brow0, M, N, K, float(alpha), _ptr(C_),
                                 self._ld(C_), 1 if tri else 0, roff, coff, self._stream())
         _lib.check(rc, "bgp_oz_gemm")
@@ -467,6 +483,16 @@ def fit(spec: KernelSpec, x: torch.Tensor, y: torch.Tensor, noise: float, *, K_o
             break
         if info == 0 and not math.isfinite(logdet):
             raise NanError("cholesky: NaN/inf encountered in the covariance matrix")
+        # a NaN pivot is reported as "not positive" by the leaf kernel: GPyTorch's psd_safe_cholesky raises NanError at once
+        # instead of burning three more N^3 factorisations on jitter retries (the factor of a failed attempt is garbage, so
+        # the inputs are what gets checked: X, the noise and one covariance entry for the hyper-parameters)
+        if attempt == 0 and kbuilder is None:
+            bad = not bool(torch.isfinite(x).all()) or not math.isfinite(noise)
+            if not bad:
+                probe = eng.cov_build(spec, x[:1], x[:1])
+                bad = not bool(torch.isfinite(probe).all())
+            if bad:
+                raise NanError("cholesky: NaN/inf encountered in the covariance matrix")
         if attempt == len(JITTERS_F64):
             raise NotPSDError(f"Matrix not positive definite after repeatedly adding jitter up to {jitter:.1e} "
                               f"(first failing pivot {info}).")

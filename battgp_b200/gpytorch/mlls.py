@@ -30,7 +30,8 @@ class _NativeLML(torch.autograd.Function):
         ctx.st, ctx.binding, ctx.n = st, binding, n
         ctx.meta = (resid.dtype, resid.device, noise.dtype, noise.device, noise.shape, [(p.dtype, p.device) for p in params])
         ctx.inverted = False
-        return torch.tensor(st.lml / n, dtype=noise.dtype, device=noise.device)
+        # GPyTorch promotes: BatteryCellGP keeps fp32 hyper-parameters next to fp64 data and its loss is fp64
+        return torch.tensor(st.lml / n, dtype=torch.promote_types(noise.dtype, resid.dtype), device=noise.device)
 
     @staticmethod
     def backward(ctx, gout):
@@ -42,7 +43,7 @@ class _NativeLML(torch.autograd.Function):
         g = eng.lml_grad(st.spec, st.noise + st.jitter, st.x, st.L, st.alpha) / n
         rd, rdev, nd, ndev, nshape, pmeta = ctx.meta
         go = gout.to(torch.float64)
-        g_noise = (g[0] * go.to(g.device)).to(device=ndev, dtype=nd).reshape(1).expand(nshape).clone() if True else None
+        g_noise = (g[0] * go.to(g.device)).to(device=ndev, dtype=nd).reshape(1).expand(nshape).clone()
         g_resid = (-st.alpha / n * go.to(st.alpha.device)).to(device=rdev, dtype=rd) if ctx.needs_input_grad[2] else None
         routed = ctx.binding.route_grads(g[1:])
         g_params = tuple((r * go.to(r.device)).to(device=dev, dtype=dt) for r, (dt, dev) in zip(routed, pmeta))
@@ -65,7 +66,7 @@ class _DenseLML(torch.autograd.Function):
         st = E.fit(E.KernelSpec([]), torch.empty(n, 1, dtype=torch.float64, device=dev), _stage(resid, dev), 0.0, kbuilder=kbuilder)
         ctx.st, ctx.n = st, n
         ctx.meta = (K.dtype, K.device, resid.dtype, resid.device)
-        return torch.tensor(st.lml / n, dtype=K.dtype, device=K.device)
+        return torch.tensor(st.lml / n, dtype=torch.promote_types(K.dtype, resid.dtype), device=K.device)
 
     @staticmethod
     def backward(ctx, gout):
@@ -103,7 +104,9 @@ class ExactMarginalLogLikelihood(MarginalLogLikelihood):
                 return _NativeLML.apply(binding, _stage(x, dev), resid, noise, *binding.param_tensors())
             K = torch_cov(cov.kernel, x, x) if torch.is_grad_enabled() else dense_cov(cov.kernel, x, x)
         else:
-            K = cov
+            # e.g. the eval-mode posterior handed back to the mll (training.py:100-103 does exactly that after fitting):
+            # log N(y; posterior mean, posterior covariance + noise), like GPyTorch's likelihood(function_dist)
+            K = cov if torch.is_tensor(cov) else cov.to_dense()
         K = K + torch.diag_embed(noise.to(K).expand(K.shape[-1]))
         return _DenseLML.apply(K, resid)
 

@@ -81,8 +81,8 @@ class CudaOps:
     def oz_slice_gather(self, P, rows, blkmap, blkrows, buf):
         return self.eng.oz_slice_gather(P, rows, blkmap, blkrows, buf)
 
-    def oz_gemm(self, buf, rows, arow0, brow0, C, K, alpha, tri, roff, coff):
-        self.eng.oz_gemm(buf, rows, arow0, buf, rows, brow0, C, K, alpha=alpha, tri=tri, roff=roff, coff=coff)
+    def oz_gemm(self, buf, rows, arow0, brow0, C, K, alpha, tri, roff, coff, tpc=0):
+        self.eng.oz_gemm(buf, rows, arow0, buf, rows, brow0, C, K, alpha=alpha, tri=tri, roff=roff, coff=coff, tpc=tpc)
 
     def trsv(self, L, dinv, b, trans):
         self.eng.trsv(L, dinv, b, trans)
@@ -111,6 +111,8 @@ class ShardedGP:
         self.dinv: Dict[int, torch.Tensor] = {}
         self.alpha: Optional[torch.Tensor] = None
         self.bytes_received = 0
+        self.lookahead = True           # one panel of look-ahead on a side stream (GPU only)
+        self.tpc_long = 4               # tiles per CTA of the long trailing updates while the side stream needs SMs
         self.profile = False            # True: synchronise after every phase and accumulate seconds in self.phase_s
         self.phase_s: Dict[str, float] = {}
 
@@ -155,11 +157,95 @@ class ShardedGP:
             blk[:, b0:e].diagonal().add_(self.noise)
             self.rows[i] = blk
 
+    # ---- streams (no-ops for the CPU checker of tests/test_sharded_cpu.py)
+    def _cuda(self):
+        return self.x.is_cuda
+
+    def _mk_streams(self):
+        if not self._cuda():
+            return None, None
+        main = torch.cuda.current_stream(self.x.device)
+        lo, hi = torch.cuda.Stream.priority_range() if hasattr(torch.cuda.Stream, "priority_range") else (0, -1)
+        return main, torch.cuda.Stream(self.x.device, priority=hi)
+
+    class _On:
+        """``with _On(stream):`` -- torch.cuda.stream(stream) on GPUs, nothing on CPU."""
+
+        def __init__(self, stream):
+            self.cm = torch.cuda.stream(stream) if stream is not None else None
+
+        def __enter__(self):
+            if self.cm is not None:
+                self.cm.__enter__()
+
+        def __exit__(self, *a):
+            if self.cm is not None:
+                self.cm.__exit__(*a)
+
+    def _panel_geometry(self, k):
+        """Who holds which rows of panel k in the packed send / rank-major gather buffers."""
+        P, NB = self.P, self.NB
+        nbelow = self.nblk - 1 - k
+        cnt_max = (nbelow + P - 1) // P
+        first = {r: next(j for j in range(k + 1, k + 1 + P) if j % P == r) for r in range(P)}
+        idx = [(j % P) * cnt_max + (j - first[j % P]) // P for j in range(k + 1, self.nblk)]
+        return nbelow, cnt_max, idx
+
+    def _update(self, k, i, c0, c1, ozbuf, panel, panel_rows, tpc=0):
+        """rows[i][:, c0:c1] -= P_i P_j^T for the columns [c0, c1) (global indices, c0 >= e_k) with panel k."""
+        if c1 <= c0:
+            return
+        ops, NB = self.ops, self.NB
+        ek, nbk = self.e(k), self.nbi(k)
+        b0i = self.b0(i)
+        C = self.rows[i][:, c0:c1]
+        if ozbuf is not None:
+            ops.oz_gemm(ozbuf, panel_rows, (i - k - 1) * NB, c0 - ek, C, nbk, -1.0, True, b0i, c0, tpc)
+        else:
+            A = panel[(i - k - 1) * NB:(i - k - 1) * NB + self.nbi(i)]
+            B = panel[c0 - ek:c1 - ek]
+            ops.gemm_nt(A, B, C, -1.0, 1.0, tri=True, roff=b0i, coff=c0)
+
     def factor(self):
+        """Right-looking over the NB-wide panels with ONE PANEL OF LOOK-AHEAD (the structure csrc/api.cu potrf_driver uses
+        on one GPU): the update of column block k+1 with panel k, the factorisation of A_k+1,k+1, its broadcast, the panel
+        solve, the all-gather and the int8 slicing of panel k+1 all run on a high-priority side stream (NCCL collectives are
+        enqueued on the stream that is current) while the main stream still applies panel k to the column blocks >= k+2.
+        ``self.profile`` (per-phase seconds) synchronises after every phase and therefore runs the same schedule serially."""
         ops, P, NB = self.ops, self.P, self.NB
         info, logdet = ops.scalars()
-        t0 = time.perf_counter()
-        for k in range(self.nblk):
+        nblk = self.nblk
+        main, side = self._mk_streams()
+        overlap = side is not None and not self.profile and getattr(self, "lookahead", True)
+        if not overlap:
+            side = None
+        use_oz_all = getattr(ops, "has_oz", False)
+        # persistent exchange buffers, double-buffered by panel parity (no allocator traffic across streams)
+        _, cnt0, _ = self._panel_geometry(0) if nblk > 1 else (0, 0, [])
+        nbk0 = self.nbi(0)
+        send_buf = [ops.empty(max(cnt0, 1) * NB, nbk0) for _ in range(2)]
+        recv_buf = [torch.empty((P * max(cnt0, 1) * NB, nbk0), dtype=send_buf[0].dtype, device=send_buf[0].device) for _ in range(2)] if P > 1 else None
+        ozbufs = [None, None]
+        ev_panel = [None, None]          # panel k gathered + sliced (side)
+        ev_u2a = [None, None]            # column block k+2 brought up to date with panel k (main)
+        ev_u2 = [None, None]             # every update with panel k issued (main): its buffers may be overwritten
+        state = {}
+
+        def record(stream):
+            if stream is None:
+                return None
+            e = torch.cuda.Event()
+            e.record(stream)
+            return e
+
+        def wait(stream, e):
+            if stream is not None and e is not None:
+                stream.wait_event(e)
+
+        def panel_chain(k):
+            """Column block k is up to date: factor A_kk, broadcast, solve the rows below, exchange, slice.  Runs on the
+            stream that is current."""
+            t0 = time.perf_counter()
             owner = k % P
             b0k, ek, nbk = self.b0(k), self.e(k), self.nbi(k)
             Lkk = ops.empty(nbk, nbk)
@@ -171,18 +257,20 @@ class ShardedGP:
                 Lkk.copy_(Akk)
             else:
                 dkk = ops.zeros_vec(ndinv)
-            if k == self.nblk - 1:
-                break
+            if k == nblk - 1:
+                return
             t0 = self._tick("diag_potrf", t0)
             self._bcast(Lkk, owner)
             self._bcast(dkk, owner)
             t0 = self._tick("bcast", t0)
             mine = [i for i in self.owned if i > k]
             nrows = sum(self.nbi(i) for i in mine)
+            nbelow, cnt_max, idx = self._panel_geometry(k)
+            b = k & 1
             # pack this rank's rows of the panel, solve them in one call, scatter back (they are part of L)
-            nbelow = self.nblk - 1 - k
-            cnt_max = (nbelow + P - 1) // P
-            send = ops.empty(cnt_max * NB, nbk)
+            send = send_buf[b][:cnt_max * NB, :nbk]
+            if send.stride(0) != nbk:                       # narrower last panels: keep the exchange buffer contiguous
+                send = send_buf[b].view(-1)[:cnt_max * NB * nbk].view(cnt_max * NB, nbk)
             if nrows:
                 o = 0
                 for i in mine:
@@ -198,49 +286,78 @@ class ShardedGP:
             t0 = self._tick("panel_trsm", t0)
             # exchange: every rank ends up with the whole panel.  The all-gather result is rank-major; the int8 path
             # slices it straight into stripe order (block map), the DMMA path needs a reordered fp64 copy.
-            use_oz = getattr(ops, "has_oz", False) and nbk % 64 == 0 and len(mine) > 0
+            use_oz = use_oz_all and nbk % 64 == 0 and len(mine) > 0
             panel = None
             panel_rows = nbelow * NB
             if P > 1:
-                assert send.is_contiguous()
-                recv = torch.empty((P * cnt_max * NB, nbk), dtype=send.dtype, device=send.device)
+                recv = recv_buf[b].view(-1)[:P * cnt_max * NB * nbk].view(P * cnt_max * NB, nbk)
                 dist.all_gather_into_tensor(recv, send, group=self.group)
                 self.bytes_received += (P - 1) * cnt_max * NB * nbk * 8
-                first = {r: next(j for j in range(k + 1, k + 1 + P) if j % P == r) for r in range(P)}
-                idx = [(j % P) * cnt_max + (j - first[j % P]) // P for j in range(k + 1, self.nblk)]
                 t0 = self._tick("allgather", t0)
                 if not mine:
                     pass                                     # this rank has no stripe below the panel: nothing to update
                 elif use_oz and hasattr(ops, "oz_slice_gather"):
-                    blkmap = torch.tensor(idx, dtype=torch.int32, device=send.device)
-                    self._ozbuf = ops.oz_slice_gather(recv, panel_rows, blkmap, NB, getattr(self, "_ozbuf", None))
+                    ozbufs[b] = ops.oz_slice_gather(recv, panel_rows, self._blkmap(k, idx, recv.device), NB, ozbufs[b])
                 else:
                     sel = torch.tensor(idx, dtype=torch.long, device=send.device)
                     panel = recv.view(P * cnt_max, NB, nbk).index_select(0, sel).view(-1, nbk)
+                    if main is not None and side is not None:
+                        panel.record_stream(main)          # allocated on the side stream, read by the main stream's updates
                     if use_oz:
-                        self._ozbuf = ops.oz_slice(panel, getattr(self, "_ozbuf", None))
-                del recv
+                        ozbufs[b] = ops.oz_slice(panel, ozbufs[b])
             else:
                 panel = send
+                panel_rows = panel.shape[0]
                 if use_oz:
-                    self._ozbuf = ops.oz_slice(panel, getattr(self, "_ozbuf", None))
-            t0 = self._tick("reorder+slice", t0)
-            for t, i in enumerate(mine):
-                b0i, ei = self.b0(i), self.e(i)
-                C = self.rows[i][:, ek:ei]
-                if use_oz:
-                    ops.oz_gemm(self._ozbuf, panel_rows if P > 1 else panel.shape[0], (i - k - 1) * NB, 0, C, nbk, -1.0, True, b0i, ek)
-                else:
-                    A = panel[(i - k - 1) * NB:(i - k - 1) * NB + self.nbi(i)]
-                    B = panel[:ei - ek]
-                    ops.gemm_nt(A, B, C, -1.0, 1.0, tri=True, roff=b0i, coff=ek)
-            t0 = self._tick("trailing_update", t0)
+                    ozbufs[b] = ops.oz_slice(panel, ozbufs[b])
+            self._tick("reorder+slice", t0)
+            state[k] = (mine, ozbufs[b] if use_oz else None, panel, panel_rows)
+
+        with self._On(side):
+            wait(side, record(main))                 # the build ran on the main stream
+            panel_chain(0)
+            ev_panel[0] = record(side)
+        for k in range(nblk - 1):
+            mine, ozb, panel, panel_rows = state.pop(k)
+            ek, ek1 = self.e(k), self.e(k + 1)
+            ek2 = self.e(k + 2) if k + 2 < nblk else ek1
+            # ---- side stream: column block k+1 <- panel k, then the whole chain of panel k+1
+            with self._On(side):
+                t0 = time.perf_counter()
+                wait(side, ev_u2a[(k - 1) & 1] if k >= 1 else None)      # block k+1 has received panel k-1 (main)
+                wait(side, ev_u2[(k - 1) & 1] if k >= 1 else None)       # buffers of parity (k+1)&1 are free again
+                for i in mine:
+                    self._update(k, i, ek, min(ek1, self.e(i)), ozb, panel, panel_rows, 1 if overlap else 0)
+                self._tick("trailing_update", t0)
+                panel_chain(k + 1)
+                ev_panel[(k + 1) & 1] = record(side)
+            # ---- main stream: the rest of the trailing update with panel k
+            t0 = time.perf_counter()
+            wait(main, ev_panel[k & 1])
+            for i in mine:
+                self._update(k, i, ek1, min(ek2, self.e(i)), ozb, panel, panel_rows, 1 if overlap else 0)
+            ev_u2a[k & 1] = record(main)
+            for i in mine:
+                self._update(k, i, ek2, self.e(i), ozb, panel, panel_rows, self.tpc_long if overlap else 0)
+            ev_u2[k & 1] = record(main)
+            self._tick("trailing_update", t0)
+            del panel
+        if side is not None:
+            main.wait_stream(side)
         self._allreduce(logdet)
         self._allreduce(info, dist.ReduceOp.MIN if dist.is_initialized() else None)
         self.logdet = float(logdet.item())
         inf = int(info.item())
         self.info = 0 if inf == INT_MAX else inf
         return self.info
+
+    def _blkmap(self, k, idx, device):
+        """int32 device map (logical stripe of panel k -> block of the rank-major gather buffer); built once per panel on
+        the host and uploaded from pinned memory without a synchronising copy."""
+        t = torch.tensor(idx, dtype=torch.int32)
+        if device.type == "cuda":
+            t = t.pin_memory().to(device, non_blocking=True)
+        return t
 
     def solve_rlt(self, Wb: Dict[int, torch.Tensor], m: int):
         """In place X <- W L^-T for W given as owned column blocks {i: [m, nb_i]}."""
@@ -356,83 +473,182 @@ class ShardedGP:
 
 
 # ------------------------------------------------------------------------------------------------------- bench
-def bench(args, rank: int, world: int, dev: torch.device):
-    """bench.py --workload sharded: BASELINE configs[4] (one GP over all ranks)."""
+def _sync(dev, world):
+    torch.cuda.synchronize(dev)
+    if world > 1:
+        dist.barrier()
+        torch.cuda.synchronize(dev)
+
+
+def _timed_steps(n, nb, rank, world, dev, steps, warmup, verify, phases, e2e=False):
+    """`steps` timed fit+predict passes of ONE GP of size n over all ranks (max over ranks, CUDA events)."""
     from .synth import query_grid, synth_field_data
     import bench as B                                    # the repo-root bench.py (flops formula, clock sampler)
-
-    n = args.n
     x_np, y_np = synth_field_data(n, seed=0)
     xq_np = query_grid(x_np, B.M_QUERY)
     x, y, xq = (torch.tensor(a, device=dev) for a in (x_np, y_np, xq_np))
+    xh, yh, xqh = (torch.tensor(a).pin_memory() for a in (x_np, y_np, xq_np))
     spec = E.battgp_spec()
     eng = E.get_engine(dev)
 
-    def step(profile=False):
-        gp = ShardedGP(spec, x, y, B.NOISE, nb=args.nb)
+    def step(profile=False, host=False):
+        if host:                                        # e2e: every rank stages the replicated inputs from pinned host memory
+            xs, ys, xqs = xh.to(dev, non_blocking=True), yh.to(dev, non_blocking=True), xqh.to(dev, non_blocking=True)
+        else:
+            xs, ys, xqs = x, y, xq
+        gp = ShardedGP(spec, xs, ys, B.NOISE, nb=nb)
         gp.profile = profile
         gp.fit()
         t0 = time.perf_counter()
-        mean, var = gp.predict(xq)
+        mean, var = gp.predict(xqs)
         gp._tick("predict", t0)
+        if host:
+            mean, var = mean.cpu(), var.cpu()
         return gp, mean, var
 
-    def sync():
-        torch.cuda.synchronize(dev)
+    def timed(nsteps, host=False):
+        _sync(dev, world)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        out = None
+        for it in range(nsteps):
+            out = None
+            out = step(host=host)
+            if it < nsteps - 1:
+                out = None
+        e1.record()
+        _sync(dev, world)
+        ms = e0.elapsed_time(e1)
         if world > 1:
-            dist.barrier()
-            torch.cuda.synchronize(dev)
+            t = torch.tensor([ms], dtype=torch.float64, device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms, out
 
-    for _ in range(args.warmup):
-        gp, mean, var = step()
-        del gp
+    for _ in range(warmup):
+        step()
         torch.cuda.empty_cache()
     sampler = B.ClockSampler(dev.index)
     if rank == 0:
         sampler.start()
     l0 = eng.launches
-    sync()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    recv = 0
-    for it in range(args.steps):
-        gp, mean, var = step()
-        recv = gp.bytes_received
-        lml = gp.lml
-        if it < args.steps - 1:
-            del gp
-    e1.record()
-    sync()
-    resid = gp.residual() if args.verify else None
-    del gp
-    phases = None
-    if args.phases:
-        torch.cuda.empty_cache()
-        gpp, _, _ = step(profile=True)
-        phases = {k: round(v, 4) for k, v in gpp.phase_s.items()}
-        del gpp
-    ms = e0.elapsed_time(e1)
-    if world > 1:
-        t = torch.tensor([ms], dtype=torch.float64, device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms = float(t.item())
+    ms, (gp, mean, var) = timed(steps)
     launches = eng.launches - l0
     clocks = sampler.stop() if rank == 0 else None
+    res = {"n": n, "nb": nb, "steps": steps, "warmup": warmup, "seconds_per_step": ms / 1e3 / steps, "lml": gp.lml,
+           "mean0": float(mean[0]), "var0": float(var[0]), "nccl_bytes_received_per_rank_per_step": gp.bytes_received,
+           "gpu_launches": int(launches), "clocks": clocks,
+           "predictions_finite_and_positive": bool(torch.isfinite(mean).all() and torch.isfinite(var).all() and (var > 0).all())}
+    res["residual_Kalpha_minus_y_over_y"] = gp.residual() if verify else None
+    del gp
+    torch.cuda.empty_cache()
+    if e2e:
+        ms_h, _ = timed(max(1, min(steps, 2)), host=True)
+        res["e2e_seconds_per_step"] = ms_h / 1e3 / max(1, min(steps, 2))
+        res["h2d_bytes_per_step"] = int(xh.numel() + yh.numel() + xqh.numel()) * 8
+    if phases:
+        torch.cuda.empty_cache()
+        gpp, _, _ = step(profile=True)
+        res["phase_seconds_rank0_serialised"] = {k: round(v, 4) for k, v in gpp.phase_s.items()}
+        del gpp
+        torch.cuda.empty_cache()
+    return res
+
+
+def parity(rank, world, dev, checker=None):
+    """Multi-rank parity, run inside the bench so that the driver's N>1 runs prove it (SURVEY 8c iii):
+    (1) n=5000 against ``checker(x, y, xq) -> (mean, var, lml)`` -- bench.py injects the CPU oracle here (this package never
+        imports it): mean rtol 1e-7, variance 1e-6, LML 1e-9;
+    (2) N=40 000: the sharded result over `world` ranks against the single-GPU engine (bgp_potrf_aug) on the same box."""
+    import numpy as np
+    from .synth import query_grid, synth_field_data
+    import bench as B
+    out = {}
+    spec = E.battgp_spec()
+    # (1) oracle
+    n1 = 5000
+    x_np, y_np = synth_field_data(n1, seed=7)
+    xq_np = query_grid(x_np, 64)
+    gp = ShardedGP(spec, torch.tensor(x_np, device=dev), torch.tensor(y_np, device=dev), B.NOISE, nb=256)
+    gp.fit()
+    mean, var = gp.predict(torch.tensor(xq_np, device=dev))
+    if rank == 0 and checker is not None:
+        mr, vr, lml_ref = checker(x_np, y_np, xq_np)
+        o = {"n": n1, "nb": 256, "mean_max_rel": float(np.max(np.abs(mean.cpu().numpy() - mr) / np.abs(mr))),
+             "var_max_rel": float(np.max(np.abs(var.cpu().numpy() - vr) / np.abs(vr))),
+             "lml_rel": abs(gp.lml - lml_ref) / abs(lml_ref), "tolerance": {"mean": 1e-7, "var": 1e-6, "lml": 1e-9}}
+        o["ok"] = bool(o["mean_max_rel"] < 1e-7 and o["var_max_rel"] < 1e-6 and o["lml_rel"] < 1e-9)
+        out["vs_cpu_oracle"] = o
+    del gp
+    # (2) rank-count invariance at N = 40 000
+    n2 = 40000
+    x_np, y_np = synth_field_data(n2, seed=0)
+    xq_np = query_grid(x_np, B.M_QUERY)
+    xd, yd, xqd = (torch.tensor(a, device=dev) for a in (x_np, y_np, xq_np))
+    gp = ShardedGP(spec, xd, yd, B.NOISE, nb=1024)
+    gp.fit()
+    mean, var = gp.predict(xqd)
+    lml = gp.lml
+    del gp
+    torch.cuda.empty_cache()
     if rank == 0:
-        sec = ms / 1e3 / args.steps
-        flops = B.algorithmic_flops(n)
-        line = {"metric": "exact_gp_fit_predict_gflops", "value": flops / sec * 1e-9, "unit": "GF/s", "n_gpus": world,
-                "steps": args.steps, "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True,
-                "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-                "config": {"workload": B.workload_name(args, world), "n": n, "m_query": B.M_QUERY, "kernel": "wiener+rbf_ard",
-                           "nb": args.nb, "fit_predict_seconds": sec, "lml": lml, "mean0": float(mean[0]), "var0": float(var[0]),
-                           "nccl_bytes_received_per_rank_per_step": recv,
-                           "residual_Kalpha_minus_y_over_y": resid, "phase_seconds_rank0_synchronised": phases,
-                           "l2_policy": "inputs_exceed_l2 (per-rank stripes rebuilt every step)"},
-                "clocks": clocks, "gpu_launches": int(launches),
-                "e2e": {"value": flops / sec * 1e-9, "unit": "GF/s", "note": "X,y replicated in HBM; host e2e measured on the per_gpu workload",
-                        "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 2 * B.M_QUERY * 8},
-                "roofline": B.step_roofline(n, sec, world, eng.ozaki)}
-        print(json.dumps(line), flush=True)
-    if world > 1:
-        dist.destroy_process_group()
+        st = E.fit(spec, xd, yd, B.NOISE, xq=xqd)
+        m1, v1 = E.predict(st, xqd)
+        o = {"n": n2, "ranks": world, "mean_max_rel": float(((mean - m1).abs() / m1.abs()).max()),
+             "var_max_rel": float(((var - v1).abs() / v1.abs()).max()), "lml_rel": abs(lml - st.lml) / abs(st.lml),
+             "alpha_note": "compared through mean/variance/LML", "tolerance": {"mean": 1e-6, "var": 1e-4, "lml": 1e-9}}
+        o["ok"] = bool(o["mean_max_rel"] < 1e-6 and o["var_max_rel"] < 1e-4 and o["lml_rel"] < 1e-9)
+        out["vs_single_gpu_engine"] = o
+        del st
+        E.get_engine(dev).release_workspace()
+    torch.cuda.empty_cache()
+    _sync(dev, world)
+    return out
+
+
+def bench_object(args, rank: int, world: int, dev: torch.device, checker=None):
+    """The "sharded" object of bench.py's N>1 line: BASELINE configs[4] timed in the same run + its parity numbers."""
+    import bench as B
+    n = args.sharded_n
+    par = parity(rank, world, dev, checker)
+    r = _timed_steps(n, 2048 if n >= 100000 else 1024, rank, world, dev, args.sharded_steps, 1, True, True)
+    if rank != 0:
+        return None
+    sec = r["seconds_per_step"]
+    flops = B.algorithmic_flops(n)
+    eng = E.get_engine(dev)
+    return {"config": {"workload": f"full_gp Wiener+RBF-ARD N={n} block-row-sharded Cholesky over {world} GPU(s), NCCL panel broadcast + "
+                                   f"all-gather, one panel of look-ahead (BASELINE configs[4])",
+                       "n": n, "m_query": B.M_QUERY, "kernel": "wiener+rbf_ard", "nb": r["nb"]},
+            "metric": B.METRIC, "value": flops / sec * 1e-9, "unit": "GF/s", "scaling": "strong", "steps": r["steps"], "warmup": r["warmup"],
+            "ms_per_step": sec * 1e3, "fit_predict_seconds": sec, "timing": "CUDA events, max over ranks, barrier on both sides",
+            "nccl_bytes_received_per_rank_per_step": r["nccl_bytes_received_per_rank_per_step"],
+            "phase_seconds_rank0_serialised": r.get("phase_seconds_rank0_serialised"),
+            "residual_Kalpha_minus_y_over_y": r["residual_Kalpha_minus_y_over_y"], "lml": r["lml"],
+            "predictions_finite_and_positive": r["predictions_finite_and_positive"],
+            "gpu_launches_per_rank": r["gpu_launches"], "parity": par, "roofline": B.step_roofline(n, sec, world, eng.ozaki)}
+
+
+def bench(args, rank: int, world: int, dev: torch.device, checker=None):
+    """bench.py --workload sharded: BASELINE configs[4] (one GP over all ranks) as the primary line."""
+    import bench as B
+    n = args.n
+    r = _timed_steps(n, args.nb, rank, world, dev, args.steps, args.warmup, args.verify, args.phases, e2e=True)
+    par = parity(rank, world, dev, checker) if (args.verify and world > 1) else None
+    if rank != 0:
+        return None
+    sec = r["seconds_per_step"]
+    flops = B.algorithmic_flops(n)
+    eng = E.get_engine(dev)
+    return {"metric": B.METRIC, "value": flops / sec * 1e-9, "unit": "GF/s", "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True,
+            "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": B.workload_config(args, world),
+            "detail": {"nb": args.nb, "fit_predict_seconds": sec, "lml": r["lml"], "mean0": r["mean0"], "var0": r["var0"],
+                       "nccl_bytes_received_per_rank_per_step": r["nccl_bytes_received_per_rank_per_step"],
+                       "residual_Kalpha_minus_y_over_y": r["residual_Kalpha_minus_y_over_y"],
+                       "phase_seconds_rank0_serialised": r.get("phase_seconds_rank0_serialised"), "parity": par},
+            "clocks": r["clocks"], "gpu_launches": r["gpu_launches"],
+            "e2e": {"value": flops / r["e2e_seconds_per_step"] * 1e-9, "unit": "GF/s", "seconds": r["e2e_seconds_per_step"],
+                    "h2d_bytes_per_step": r["h2d_bytes_per_step"], "d2h_bytes_per_step": 2 * B.M_QUERY * 8,
+                    "note": "every rank stages the replicated X, y, X* from pinned host memory and reads mean/variance back"},
+            "roofline": B.step_roofline(n, sec, world, eng.ozaki)}

@@ -288,6 +288,14 @@ def _init_dist(n_gpus: int):
     return rank, local_rank, world, dev
 
 
+def _oracle_checker(x, y, xq):
+    """CPU oracle as the CHECKER of the sharded parity numbers (never on the measured path)."""
+    from oracle import gp_oracle as orc
+    f = orc.fit(orc.battgp_spec(), x, y, NOISE)
+    m, v = orc.predict(orc.battgp_spec(), x, f, xq)
+    return m, v, f.lml
+
+
 def run_gpu(args, n_gpus: int):
     import torch
     import torch.distributed as dist
@@ -297,7 +305,7 @@ def run_gpu(args, n_gpus: int):
     rank, local_rank, world, dev = _init_dist(n_gpus)
     if args.workload == "sharded":
         from battgp_b200 import sharded
-        line = sharded.bench(args, rank, world, dev)
+        line = sharded.bench(args, rank, world, dev, checker=_oracle_checker)
         if rank == 0:
             print(json.dumps(line), flush=True)
         if world > 1:
@@ -387,7 +395,7 @@ def run_gpu(args, n_gpus: int):
         eng.release_workspace()
         torch.cuda.empty_cache()
         from battgp_b200 import sharded
-        sharded_obj = sharded.bench_object(args, rank, world, dev)
+        sharded_obj = sharded.bench_object(args, rank, world, dev, checker=_oracle_checker)
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()

@@ -72,7 +72,7 @@ void bgp_ctx_destroy(bgp_ctx* ctx);
 /* tuning knobs: "nb" uniform outer panel width (multiple of 128; 0 = automatic schedule: the width follows the rows still to
  * be factorised -- 512 below "sched_t1024" rows, 1024 from there, 2048 from "sched_t2048" and 4096 from "sched_t4096" on the
  * int8 path, "sched_w0"/"sched_w1" cap the first two panels), "lookahead" 0/1, "ozaki" 0/1 (trailing updates on the int8
- * tcgen05 path, fp64-accurate), "oz_tpc"/"oz_cluster" (tiles per CTA / cluster size of that kernel), "gemm_cfg" (probing),
+ * tcgen05 path, fp64-accurate), "oz_tpc"/"oz_tpc_gemm"/"oz_cluster"/"oz_group" (tiles per CTA inside bgp_potrf / in stand-alone bgp_oz_gemm calls, 0 = one persistent CTA per SM; cluster size; tile rows per raster group of that kernel), "gemm_cfg" (probing),
  * "pdl" 0/1 (programmatic dependent launch of the dependent-kernel chains: triangular sweeps, leaf + small GEMMs), "trace" 0/1 (bgp_potrf prints a per-panel event timeline to stderr; diagnostics). returns 0 or BGP_E_ARG */
 int  bgp_ctx_set(bgp_ctx* ctx, const char* key, int value);
 /* Optional scratch for bgp_potrf's int8/tcgen05 trailing updates ("ozaki" knob, csrc/ozaki.cu): the caller (torch)
@@ -84,6 +84,12 @@ int  bgp_panel_schedule(int64_t rows, int64_t n, int ozaki, int nb, int64_t* sta
 int  bgp_ctx_set_workspace(bgp_ctx* ctx, void* ptr, int64_t bytes);
 /* counts kernels launched through this context since creation (bench.py's gpu_launches) */
 int64_t bgp_ctx_launches(const bgp_ctx* ctx);
+/* Measurement hook (bench.py's roofline): while enabled, bgp_potrf / bgp_potrf_aug bracket every trailing-update launch of the
+ * int8/tcgen05 kernel (csrc/ozaki.cu oz_mma_kernel) with timed CUDA events on the stream it is launched on.
+ * bgp_ctx_kernel_profile_read waits for the recorded launches, returns their summed duration (ms), summed algorithmic flop
+ * (2 x computed lower-triangle area x panel width) and count, and clears the record.  Enabling also clears it. */
+int bgp_ctx_kernel_profile(bgp_ctx* ctx, int enable);
+int bgp_ctx_kernel_profile_read(bgp_ctx* ctx, double* ms, double* flop, int64_t* launches);
 
 /* ---- K1+K2+K3: fused covariance build -------------------------------------------------------------
  * replaces WienerKernel.forward (wiener_kernel.py:10-32), RBFKernel/ScaleKernel/+ (cell_gp.py:33-36) and the
@@ -110,7 +116,7 @@ int bgp_gemm_nt(bgp_ctx* ctx, int64_t M, int64_t N, int64_t K, double alpha,
                 double beta, double* C, int64_t ldc, int tri, int64_t roff, int64_t coff, void* stream);
 
 /* EXPERIMENTAL: same contraction with C += alpha * A * B^T evaluated by int8 slicing on the tcgen05 tensor cores
- * (Ozaki scheme, fp64-accurate; csrc/ozaki.cu).  K must be a multiple of 64.  work: device scratch of
+ * (Ozaki scheme, fp64-accurate; csrc/ozaki.cu).  K must be a multiple of 64 and <= 16384 (BGP_E_ARG otherwise).  work: device scratch of
  * bgp_gemm_nt_i8_work_bytes(M, N, K) bytes, 256-byte aligned. */
 int64_t bgp_gemm_nt_i8_work_bytes(int64_t M, int64_t N, int64_t K);
 int bgp_gemm_nt_i8(bgp_ctx* ctx, int64_t M, int64_t N, int64_t K, double alpha,
@@ -119,7 +125,7 @@ int bgp_gemm_nt_i8(bgp_ctx* ctx, int64_t M, int64_t N, int64_t K, double alpha,
                    void* work, int64_t work_bytes, void* stream);
 
 /* The two halves of bgp_gemm_nt_i8, for callers that re-use one sliced panel for many products (sharded trailing update):
- * bgp_oz_slice: rows x K fp64 (K % 64 == 0) -> 8 int8 digit planes + per-row scales in buf (bgp_oz_slice_bytes, 256-B aligned).
+ * bgp_oz_slice: rows x K fp64 (K % 64 == 0, K <= 16384: the int32 accumulators of bgp_oz_gemm hold 7 K 2^14) -> 7 int8 digit planes + per-row scales in buf (bgp_oz_slice_bytes, 256-B aligned).
  * bgp_oz_gemm : C[M,N] += alpha * A B^T with A = rows arow0.. (multiple of 128) of bufA, B = rows brow0.. (multiple of 64) of bufB. */
 int64_t bgp_oz_slice_bytes(int64_t rows, int64_t K);
 int bgp_oz_slice(bgp_ctx* ctx, const double* P, int64_t rows, int64_t K, int64_t ld, void* buf, int64_t buf_bytes, void* stream);

@@ -1,4 +1,6 @@
-"""CPU: bench.py's reference arm (the CPU restatement timed on the host cores) produces the contract's JSON line."""
+"""CPU: bench.py's reference arm (the reference's CPU path restated in torch fp64, timed on the host cores) produces the
+contract's JSON line, with a `config` object identical to the one the B200 arm prints for the same flags."""
+import argparse
 import json
 import os
 import subprocess
@@ -7,19 +9,41 @@ import sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-def test_reference_arm_json_contract():
-    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0",
-                          "--ref-n", "400"], capture_output=True, text=True, timeout=300, cwd=ROOT)
+def _run(*flags):
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", *flags],
+                         capture_output=True, text=True, timeout=300, cwd=ROOT)
     assert out.returncode == 0, out.stderr
-    line = json.loads(out.stdout.strip().splitlines()[-1])
-    for key in ("impl", "metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling",
+    return json.loads(out.stdout.strip().splitlines()[-1])
+
+
+def test_reference_arm_json_contract():
+    line = _run("--steps", "2", "--warmup", "0", "--size", "400")
+    for key in ("impl", "metric", "value", "unit", "n_gpus", "steps", "steps_run", "warmup", "ms_per_step", "higher_is_better", "scaling",
                 "vs_baseline", "dtype", "data", "config", "cpu_baseline", "e2e"):
         assert key in line, key
     assert line["impl"] == "reference" and line["metric"] == "exact_gp_fit_predict_gflops" and line["unit"] == "GF/s"
     assert line["dtype"] == "f64" and line["data"] == "synthetic" and line["vs_baseline"] is None
     assert "workload" in line["config"] and "model" not in line["config"]
+    assert line["steps"] == 2 and 1 <= line["steps_run"] <= 2
     assert line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["cores"] >= 1
+    assert "torch fp64" in line["cpu_baseline"]["sample"] and "cholesky_ex" in line["cpu_baseline"]["sample"]
     assert line["e2e"]["h2d_bytes_per_step"] == 0 and line["e2e"]["value"] == line["value"] > 0
+
+
+def test_reference_arm_config_equals_the_b200_arm_config():
+    """The driver compares the two arms' `config`: it must describe the workload only (nothing measured, no sample size)."""
+    sys.path.insert(0, ROOT)
+    import bench
+    line = _run("--steps", "1", "--warmup", "0", "--size", "300", "--gpus", "1")
+    args = argparse.Namespace(n=300, workload="per_gpu")
+    assert line["config"] == bench.workload_config(args, 1)
+    assert set(line["config"]) == {"workload", "n", "m_query", "kernel", "l2_policy"}
+    # the default size is BASELINE configs[1] and the reference arm then really runs N = 40 000
+    d = bench.workload_config(argparse.Namespace(n=40000, workload="per_gpu"), 1)
+    assert "N=40000" in d["workload"] and "configs[1]" in d["workload"]
+    assert "configs[3]" in bench.workload_config(argparse.Namespace(n=40000, workload="per_gpu"), 8)["workload"]
+    assert "configs[4]" in bench.workload_config(argparse.Namespace(n=200000, workload="sharded"), 8)["workload"]
+    assert "configs[2]" in bench.workload_config(argparse.Namespace(n=80000, workload="train"), 1)["workload"]
 
 
 def test_flop_model():
@@ -27,5 +51,6 @@ def test_flop_model():
     import bench
     n, m = 40000, 300
     assert abs(bench.algorithmic_flops(n, m) - (n ** 3 / 3 + n * n * m + 2 * n * n)) < 1.0
-    r = bench.step_roofline(200000, 5.79, 8, True)
+    r = bench.step_roofline(200000, 4.0, 8, True)
     assert r["bound"] == "tensor" and 0.3 < r["frac"] < 1.0 and r["fp64_equivalent_over_dmma_peak"] > 1.0
+    assert bench.OZ_PAIRS == 28
