@@ -67,6 +67,8 @@ SIGNATURES = {
     "bgp_potrf_dinv_elems": (_I64, [_I64]),
     "bgp_potrf": (C.c_int, [_P, _P, _I64, _I64, _P, C.POINTER(_D), _P]),
     "bgp_potrf_aug": (C.c_int, [_P, _P, _I64, _I64, _I64, _P, C.POINTER(_D), _P]),
+    "bgp_potrf_async": (C.c_int, [_P, _P, _I64, _I64, _I64, _P, _P, _P, _P]),
+    "bgp_lml_dev": (C.c_int, [_P, _P, _I64, _P, _P, _P]),
     "bgp_potrf_block": (C.c_int, [_P, _P, _I64, _I64, _P, _P, _P, _P]),
     "bgp_potrs_vec": (C.c_int, [_P, _P, _I64, _I64, _P, _P, _P, _P, _P]),
     "bgp_trsm_rlt": (C.c_int, [_P, _P, _I64, _I64, _P, _P, _I64, _I64, _P]),
@@ -75,6 +77,7 @@ SIGNATURES = {
     "bgp_trsv": (C.c_int, [_P, _P, _I64, _I64, _P, _P, C.c_int, _P]),
     "bgp_gemv_t": (C.c_int, [_P, _P, _I64, _I64, _I64, _P, _P, _D, _P]),
     "bgp_rowsumsq": (C.c_int, [_P, _P, _I64, _I64, _I64, _P, C.c_int, _P]),
+    "bgp_fault_eval": (C.c_int, [_P, _P, _P, _I64, _I64, _I64, _D, _D, _P, _P, _P, _P, _P, _P, _P, _P]),
     "bgp_potri": (C.c_int, [_P, _P, _I64, _I64, _P, _P, _I64, _P]),
     "bgp_lml_grad": (C.c_int, [_P, _SPEC, _P, _I64, _I64, _P, _I64, _P, _P, _P]),
 }

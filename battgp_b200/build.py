@@ -10,7 +10,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIBDIR = os.path.join(HERE, "lib")
 LIBPATH = os.path.join(LIBDIR, "libbattgp_b200.so")
-SOURCES = ["api.cu", "gemm_nt.cu", "potrf.cu", "cov_build.cu", "solve.cu", "grad.cu", "ozaki.cu", "ozaki2.cu", "next/ozaki2_mma.cu"]
+SOURCES = ["api.cu", "gemm_nt.cu", "potrf.cu", "cov_build.cu", "solve.cu", "grad.cu", "ozaki.cu", "ozaki2.cu", "next/ozaki2_mma.cu", "fault.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-shared", "-Xcompiler", "-fPIC"]
 

@@ -36,9 +36,19 @@ int potri(Ctx*, double*, int64_t, int64_t, const double*, double*, int64_t, cuda
 int lml_grad(Ctx*, const bgp_kernel_spec*, const double*, int64_t, int64_t, const double*, int64_t, const double*,
              double*, cudaStream_t);
 
+int fault_eval(Ctx*, const double*, const double*, int64_t, int64_t, int64_t, double, double, double*, double*, double*, double*, double*,
+               double*, double*, cudaStream_t);
 void leaf_clk_read(long long* out);
 __global__ void init_scalars_kernel(int32_t* info, double* scal) {
     if (threadIdx.x == 0) { *info = INT_MAX; scal[0] = 0.0; }
+}
+
+__global__ void init_scalars_at_kernel(int32_t* info, double* logdet) {
+    if (threadIdx.x == 0) { *info = INT_MAX; *logdet = 0.0; }
+}
+// lml = -0.5 z.z - 0.5 logdet - 0.5 n log(2 pi), everything on the device (bgp_lml_dev)
+__global__ void lml_finish_kernel(const double* zz, const double* logdet, double n, double* out) {
+    if (threadIdx.x == 0) *out = -0.5 * zz[0] - 0.5 * logdet[0] - 0.5 * n * 1.8378770664093454835606594728112;
 }
 
 struct DeviceGuard {
@@ -441,6 +451,38 @@ int bgp_potrf_aug(bgp_ctx* c, double* A, int64_t n, int64_t mx, int64_t lda, dou
     return info == INT_MAX ? 0 : (int)info;
 }
 
+int bgp_potrf_async(bgp_ctx* c, double* A, int64_t n, int64_t mx, int64_t lda, double* dinv, int32_t* info_dev, double* logdet_dev,
+                    void* stream) {
+    CTX_OR_FAIL(c);
+    if (n < 0 || mx < 0 || n + mx > INT_MAX || !info_dev || !logdet_dev) return BGP_E_ARG;
+    if (n == 0) return 0;
+    if (!A || !dinv || lda < n) return BGP_E_ARG;
+    cudaStream_t st = (cudaStream_t)stream;
+    init_scalars_at_kernel<<<1, 32, 0, st>>>(info_dev, logdet_dev);
+    BGP_LAUNCH_OK(ctx);
+    // single stream, no look-ahead, nothing read back: the recursive factorisation with the leaf outputs redirected
+    int32_t* si = ctx->d_info;
+    double* ss = ctx->d_scal;
+    ctx->d_info = info_dev;
+    ctx->d_scal = logdet_dev;
+    int rc = potrf_rec(ctx, A, n, lda, dinv, 0, st);
+    if (!rc && mx > 0) rc = trsm_rlt_rec(ctx, A, n, lda, dinv, A + n * lda, mx, lda, st);
+    ctx->d_info = si;
+    ctx->d_scal = ss;
+    return rc;
+}
+
+int bgp_lml_dev(bgp_ctx* c, const double* z, int64_t n, const double* logdet_dev, double* lml_dev, void* stream) {
+    CTX_OR_FAIL(c);
+    if (!lml_dev || !logdet_dev || n <= 0 || !z) return BGP_E_ARG;
+    cudaStream_t st = (cudaStream_t)stream;
+    int rc = dot(ctx, z, z, n, ctx->d_scal + 8, ctx->d_scal + 1, st);
+    if (rc) return rc;
+    lml_finish_kernel<<<1, 32, 0, st>>>(ctx->d_scal + 1, logdet_dev, (double)n, lml_dev);
+    BGP_LAUNCH_OK(ctx);
+    return 0;
+}
+
 int bgp_potrf_block(bgp_ctx* c, double* A, int64_t nb, int64_t lda, double* dinv, int32_t* info_dev, double* logdet_dev,
                     void* stream) {
     CTX_OR_FAIL(c);
@@ -610,6 +652,17 @@ int bgp_oz2_gemm(bgp_ctx* c, int64_t M, int64_t N, int64_t K, double alpha, cons
     if (!A || !B || !C || !work || lda < K || ldb < K || ldc < N || work_bytes < oz2_gemm_work_bytes(M, N, K) || ((uintptr_t)work & 255))
         return BGP_E_ARG;
     return oz2_gemm(ctx, A, M, lda, B, N, ldb, K, alpha, C, ldc, work, (cudaStream_t)stream);
+}
+
+int bgp_fault_eval(bgp_ctx* c, const double* r0, const double* r0var, int64_t M, int64_t C, int64_t ld, double band, double threshold,
+                   double* p_outside, double* p_above, double* p_below, double* r0_mean, double* p_threshold, double* cells_var,
+                   double* weakest_link, void* stream) {
+    CTX_OR_FAIL(c);
+    if (M < 0 || C < 2 || C > 16 || ld < C) return BGP_E_ARG;
+    if (M == 0) return 0;
+    if (!r0 || !r0var || !p_outside || !p_above || !p_below || !r0_mean || !p_threshold || !cells_var || !weakest_link) return BGP_E_ARG;
+    return fault_eval(ctx, r0, r0var, M, C, ld, band, threshold, p_outside, p_above, p_below, r0_mean, p_threshold, cells_var, weakest_link,
+                      (cudaStream_t)stream);
 }
 
 int bgp_potri(bgp_ctx* c, double* L, int64_t n, int64_t ldl, const double* dinv, double* work, int64_t ldw,

@@ -332,6 +332,20 @@ class Engine:
         _lib.check(rc, "bgp_potrf_aug")
         return rc, logdet.value, dinv
 
+    def potrf_async(self, A: torch.Tensor, info_dev: torch.Tensor, logdet_dev: torch.Tensor) -> torch.Tensor:
+        """Asynchronous in-place Cholesky of an n x n or (n + mx) x n matrix (small systems; no host sync, results stay on
+        the device): returns the 128-block inverses."""
+        n = A.shape[1]
+        mx = A.shape[0] - n
+        dinv = torch.empty(int(self.L.bgp_potrf_dinv_elems(n)), dtype=torch.float64, device=self.device)
+        rc = self.L.bgp_potrf_async(self.h, _ptr(A), n, mx, self._ld(A), _ptr(dinv), _ptr(info_dev), _ptr(logdet_dev), self._stream())
+        _lib.check(rc, "bgp_potrf_async")
+        return dinv
+
+    def lml_dev(self, z: torch.Tensor, logdet_dev: torch.Tensor, out: torch.Tensor) -> torch.Tensor:
+        _lib.check(self.L.bgp_lml_dev(self.h, _ptr(z), z.shape[0], _ptr(logdet_dev), _ptr(out), self._stream()), "bgp_lml_dev")
+        return out
+
     # ------------------------------------------------------------------ K5
     def potrs_vec(self, Lm: torch.Tensor, dinv: torch.Tensor, y: torch.Tensor):
         n = Lm.shape[0]
@@ -354,11 +368,11 @@ class Engine:
         _lib.check(rc, "bgp_trsm_rlt")
         return X
 
-    def predict_tail(self, Kq=None, alpha=None, V=None, kdiag=None, min_var=MIN_VARIANCE_F64):
+    def predict_tail(self, Kq=None, alpha=None, V=None, kdiag=None, min_var=MIN_VARIANCE_F64, mean_out=None, var_out=None):
         ref = Kq if Kq is not None else V
         m, n = ref.shape
-        mean = torch.empty(m, dtype=torch.float64, device=self.device) if Kq is not None else None
-        var = torch.empty(m, dtype=torch.float64, device=self.device) if V is not None else None
+        mean = (mean_out if mean_out is not None else torch.empty(m, dtype=torch.float64, device=self.device)) if Kq is not None else None
+        var = (var_out if var_out is not None else torch.empty(m, dtype=torch.float64, device=self.device)) if V is not None else None
         rc = self.L.bgp_predict_tail(self.h, m, n, _ptr(Kq), self._ld(Kq) if Kq is not None else 0, _ptr(alpha),
                                      _ptr(V), self._ld(V) if V is not None else 0, _ptr(kdiag), float(min_var),
                                      _ptr(mean), _ptr(var), self._stream())

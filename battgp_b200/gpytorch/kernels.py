@@ -485,8 +485,11 @@ class AdditiveKernel(Kernel):
 
 
 class MultiDeviceKernel(Kernel):
-    """cell_gp.py:38-43.  GPyTorch scatters kernel blocks over devices with DataParallel; here one GP's factorisation is
-    sharded by battgp_b200.sharded instead, so this wrapper only forwards to ``base_kernel``."""
+    """cell_gp.py:38-43.  GPyTorch scatters kernel blocks over devices with DataParallel inside one process; here ONE GP's
+    factorisation is block-row-sharded over one process per GPU (battgp_b200/sharded.py): an ExactGP whose kernel is a
+    MultiDeviceKernel with more than one device id takes that path in eval mode when the program runs under torchrun with a
+    process group of that many ranks (gpytorch/models.py _sharded_world), and warns + stays on one GPU otherwise.  The
+    covariance itself is ``base_kernel``'s."""
 
     def __init__(self, base_kernel, device_ids, output_device=None, **kwargs):
         super().__init__()
@@ -499,7 +502,66 @@ class MultiDeviceKernel(Kernel):
 
 
 class InducingPointKernel(Kernel):
-    """standard_models.py:83 (SGPR): an approximate method outside the exact-GP path."""
+    """standard_models.py:83-87 (SparseScaledRBFModel, SGPR): the subset-of-regressors covariance through m inducing points u,
+        k_Q(x1, x2) = K_x1,u K_uu^-1 K_u,x2,
+    which is what GPyTorch's InducingPointKernel returns in eval mode (a low-rank root); in training mode the diagonal of the
+    train block is corrected to the exact prior variance (FITC-style ``LowRankRootAddedDiagLinearOperator``).  Here the factor
+    A = K_xu L_uu^-T is formed with the engine (bgp_potrf, bgp_trsm_rlt, bgp_gemm_nt) and the N x N matrix Q = A A^T is handed to
+    the exact path as a dense covariance: the posterior mean / variance equal GPyTorch's SGPR prediction, computed with the
+    O(N^3) exact factorisation instead of the O(N m^2) Woodbury form (SGPR is an approximate method outside the hot path,
+    SURVEY.md section 2 row 4 -- supported for completeness of the reference surface, not optimised).  The variational trace
+    term GPyTorch adds to the MLL for learning the inducing points is not implemented (the reference never trains this
+    model: its ``optimize`` calls a function that does not exist)."""
 
-    def __init__(self, *a, **k):
-        raise NotImplementedError("InducingPointKernel (SGPR) is out of scope of the exact-GP engine")
+    def __init__(self, base_kernel, inducing_points, likelihood, active_dims=None, **kwargs):
+        super().__init__(active_dims=active_dims)
+        self.base_kernel = base_kernel
+        self.likelihood = likelihood
+        if inducing_points.dim() == 1:
+            inducing_points = inducing_points.unsqueeze(-1)
+        self.register_parameter("inducing_points", torch.nn.Parameter(inducing_points))
+
+    def _root(self, x: torch.Tensor, Luu: torch.Tensor, dinv: torch.Tensor, dev) -> torch.Tensor:
+        """A = K_xu L_uu^-T  [n, m], fp64 on the compute device."""
+        eng = E.get_engine(dev)
+        Kxu = E.alloc_matrix(x.shape[0], self.inducing_points.shape[0], dev)
+        Kxu.copy_(dense_cov(self.base_kernel, x, self.inducing_points.to(x)).to(device=dev, dtype=torch.float64))
+        return eng.trsm_rlt(Luu, dinv, Kxu)
+
+    def forward(self, x1, x2, diag=False, **params):
+        dev = compute_device(x1)
+        eng = E.get_engine(dev)
+        u = self.inducing_points.detach()
+        m = u.shape[0]
+        Kuu = E.alloc_matrix(m, m, dev)
+        Kuu.copy_(dense_cov(self.base_kernel, u, u).to(device=dev, dtype=torch.float64))
+        jitter = 0.0
+        for attempt in range(len(E.JITTERS_F64) + 1):          # psd_safe_cholesky of K_uu
+            L = Kuu.clone()
+            if jitter:
+                L.diagonal().add_(jitter)
+            info, _, dinv = eng.potrf(L)
+            if info == 0:
+                break
+            if attempt == len(E.JITTERS_F64):
+                raise E.NotPSDError("inducing-point covariance K_uu is not positive definite")
+            jitter = E.JITTERS_F64[attempt]
+        same = x1 is x2 or (x1.shape == x2.shape and torch.equal(x1, x2))
+        A1 = self._root(x1, L, dinv, dev)
+        A2 = A1 if same else self._root(x2, L, dinv, dev)
+        if diag:
+            out = torch.empty(x1.shape[0], dtype=torch.float64, device=dev)
+            if same:
+                eng.rowsumsq(A1, out, False)
+            else:
+                out = (A1 * A2).sum(-1)
+            if self.training and same:
+                out = torch.maximum(out, dense_cov_diag(self.base_kernel, x1).to(device=dev, dtype=torch.float64))
+            return out.to(device=x1.device, dtype=x1.dtype)
+        Q = E.alloc_matrix(x1.shape[0], x2.shape[0], dev)
+        eng.gemm_nt(A1, A2, Q, alpha=1.0, beta=0.0)
+        if self.training and same:
+            kd = dense_cov_diag(self.base_kernel, x1).to(device=dev, dtype=torch.float64)
+            corr = (kd - Q.diagonal()).clamp_min(0.0)
+            Q.diagonal().add_(corr)
+        return Q.to(device=x1.device, dtype=x1.dtype)

@@ -85,6 +85,51 @@ class PosteriorCovariance:
         return c + torch.diag_embed(noise.to(c).expand(c.shape[-1]))
 
 
+class ShardedPosteriorCovariance:
+    """Posterior covariance of a GP that was factorised by battgp_b200.sharded over several GPUs: the variance is already
+    reduced over the ranks; the dense M x M covariance is not formed in this mode."""
+
+    def __init__(self, var: torch.Tensor):
+        self._var = var
+
+    @property
+    def shape(self):
+        m = self._var.shape[0]
+        return torch.Size([m, m])
+
+    def diagonal(self, *a, **k):
+        return self._var
+
+    diag = diagonal
+
+    def to_dense(self):
+        raise NotImplementedError("the full predictive covariance is not available for a GP sharded over several GPUs "
+                                  "(MultiDeviceKernel with n_devices > 1); read .mean / .variance")
+
+    evaluate = to_dense
+
+
+def _sharded_world(kernel) -> int:
+    """cell_gp.py:38-43: BatteryCellGP(n_devices > 1) wraps its kernel in MultiDeviceKernel.  GPyTorch scatters kernel blocks
+    with DataParallel inside ONE process; this engine runs one process per GPU, so the knob maps to the block-row-sharded
+    factorisation (battgp_b200/sharded.py) when the program was launched with torchrun and the process group spans
+    ``n_devices`` ranks.  Returns that world size, or 0 for the single-GPU path."""
+    from .kernels import MultiDeviceKernel
+    if not isinstance(kernel, MultiDeviceKernel) or len(kernel.device_ids) <= 1:
+        return 0
+    import torch.distributed as dist
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+        if dist.get_world_size() != len(kernel.device_ids):
+            raise RuntimeError(f"MultiDeviceKernel(device_ids={kernel.device_ids}) asks for {len(kernel.device_ids)} GPUs but the process "
+                               f"group has {dist.get_world_size()} ranks: launch one process per GPU (torchrun --nproc-per-node "
+                               f"{len(kernel.device_ids)}), see INTEGRATION.md 'One GP over several GPUs'")
+        return dist.get_world_size()
+    warnings.warn(f"MultiDeviceKernel over {len(kernel.device_ids)} devices: battgp_b200 shards ONE GP across GPUs with one process "
+                  "per GPU (torchrun + battgp_b200.sharded, INTEGRATION.md); in this single-process run the factorisation stays on "
+                  "one GPU (same results, single-GPU memory limit)", RuntimeWarning)
+    return 0
+
+
 class ExactGP(GP):
     def __init__(self, train_inputs, train_targets, likelihood):
         if train_inputs is not None and torch.is_tensor(train_inputs):
@@ -157,6 +202,31 @@ class ExactGP(GP):
         self.prediction_strategy = (sig, st, kernel)
         return st, kernel
 
+    def _sharded_call(self, kernel, xq, inputs, kwargs):
+        """Eval-mode call of a model whose kernel is MultiDeviceKernel(n_devices = world size): every rank runs this same call
+        (SPMD) with the same data; the N x N factorisation is block-row-sharded over the ranks (battgp_b200/sharded.py)."""
+        from ..sharded import ShardedGP
+        train_x = self.train_inputs[0]
+        binding = bind_spec(kernel, train_x.shape[-1])
+        if binding is None:
+            raise RuntimeError("MultiDeviceKernel over several GPUs needs a kernel the engine builds natively "
+                               "(Wiener / RBF / Matern-5/2 / Periodic under ScaleKernel, summed)")
+        dev = compute_device(train_x)
+        sig = self._signature()
+        if self.prediction_strategy is None or self.prediction_strategy[0] != ("sharded", sig):
+            prior = self.forward(*self.train_inputs)
+            resid = _stage(self.train_targets - prior.mean, dev)
+            noise = float(self.likelihood.noise.detach().reshape(-1)[0])
+            n = train_x.shape[0]
+            gp = ShardedGP(binding.to_spec(), _stage(train_x, dev), resid, noise, nb=2048 if n >= 100000 else 1024)
+            gp.fit()
+            self.prediction_strategy = (("sharded", sig), gp, kernel)
+        gp = self.prediction_strategy[1]
+        test_prior = self.forward(*inputs, **kwargs)
+        mean, var = gp.predict(_stage(xq, dev), clamp=False)
+        mean = mean.to(device=xq.device, dtype=xq.dtype) + test_prior.mean
+        return MultivariateNormal(mean, ShardedPosteriorCovariance(var.to(device=xq.device, dtype=xq.dtype)))
+
     def __call__(self, *args, **kwargs):
         inputs = [a.unsqueeze(-1) if a.dim() == 1 else a for a in args]
         if self.training:
@@ -172,6 +242,9 @@ class ExactGP(GP):
         if settings.debug.on() and all(a.shape == b.shape and torch.equal(a, b) for a, b in zip(self.train_inputs, inputs)):
             warnings.warn("The input matches the stored training data. Did you forget to call model.train()?", GPInputWarning)
         xq = inputs[0]
+        prior_cov = self.forward(*self.train_inputs)._covar
+        if isinstance(prior_cov, LazyKernelMatrix) and _sharded_world(prior_cov.kernel):
+            return self._sharded_call(prior_cov.kernel, xq, inputs, kwargs)
         st, kernel = self._fit_state(xq)
         test_prior = self.forward(*inputs, **kwargs)
         dev = st.x.device

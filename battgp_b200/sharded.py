@@ -111,7 +111,8 @@ class ShardedGP:
         self.dinv: Dict[int, torch.Tensor] = {}
         self.alpha: Optional[torch.Tensor] = None
         self.bytes_received = 0
-        self.lookahead = True           # one panel of look-ahead on a side stream (GPU only)
+        import os as _os
+        self.lookahead = _os.environ.get("BATTGP_SHARDED_LOOKAHEAD", "1") != "0"   # one panel of look-ahead on a side stream (GPU only)
         self.tpc_long = 4               # tiles per CTA of the long trailing updates while the side stream needs SMs
         self.profile = False            # True: synchronise after every phase and accumulate seconds in self.phase_s
         self.phase_s: Dict[str, float] = {}

@@ -284,7 +284,8 @@ def _init_dist(n_gpus: int):
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
+        import datetime
+        dist.init_process_group("nccl", device_id=dev, timeout=datetime.timedelta(seconds=600))
     return rank, local_rank, world, dev
 
 
@@ -395,7 +396,10 @@ def run_gpu(args, n_gpus: int):
         eng.release_workspace()
         torch.cuda.empty_cache()
         from battgp_b200 import sharded
-        sharded_obj = sharded.bench_object(args, rank, world, dev, checker=_oracle_checker)
+        try:
+            sharded_obj = sharded.bench_object(args, rank, world, dev, checker=_oracle_checker)
+        except Exception as e:          # the per-GPU line above stays valid; the failure is reported, not hidden
+            sharded_obj = {"error": f"{type(e).__name__}: {e}"[:800]}
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()

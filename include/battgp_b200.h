@@ -166,6 +166,14 @@ int bgp_potrf(bgp_ctx* ctx, double* A, int64_t n, int64_t lda, double* dinv, dou
  * panel solves / trailing updates of the factorisation.  Workspace: bgp_potrf_workspace_bytes(ctx, n + mx). */
 int bgp_potrf_aug(bgp_ctx* ctx, double* A, int64_t n, int64_t mx, int64_t lda, double* dinv, double* logdet_host, void* stream);
 
+/* Fully asynchronous form for SMALL systems (the reference's default N = 1000 per cell, 9 GPs per battery: battgp_full.py:41-60,
+ * config.py:29): single stream, no look-ahead, info (INT_MAX = ok, else 1-based failing pivot) and logdet stay on the device,
+ * no host synchronisation -- several independent GPs can be in flight on different streams (one bgp_ctx each) or be captured in
+ * a CUDA graph (battgp_b200/batch.py).  bgp_lml_dev is bgp_lml without the read-back: lml_dev <- LML. */
+int bgp_potrf_async(bgp_ctx* ctx, double* A, int64_t n, int64_t mx, int64_t lda, double* dinv, int32_t* info_dev, double* logdet_dev,
+                    void* stream);
+int bgp_lml_dev(bgp_ctx* ctx, const double* z, int64_t n, const double* logdet_dev, double* lml_dev, void* stream);
+
 /* ---- K5: alpha = K^-1 y via two triangular sweeps (HBM-bound) -------------------------------------------
  * replaces cholesky_solve for the mean cache of DefaultPredictionStrategy / inv_quad of the mll.
  * y [n] in, z = L^-1 y written to z [n] (may be NULL), alpha = L^-T z written to alpha [n]. */
@@ -198,6 +206,15 @@ int bgp_potri(bgp_ctx* ctx, double* L, int64_t n, int64_t ldl, const double* din
               void* stream);
 int bgp_lml_grad(bgp_ctx* ctx, const bgp_kernel_spec* spec, const double* X, int64_t n, int64_t ldx,
                  const double* Kinv, int64_t ldk, const double* alpha, double* grad_dev, void* stream);
+
+/* ---- output side: fault evaluation of a battery on the device -----------------------------------------------
+ * replaces get_fault_evaluation / calc_outside_band_probabilities(band_mean_without_eval_cell=True) / calc_over_threshold_probability /
+ * calc_r0_cells_var (/root/reference/src/batt_models/fault_evaluation.py:20-104) and the weakest-link statistic
+ * (fault_probabilities.py:88-95) on r0, r0var [M, ld] (M query times x C cells, 2 <= C <= 16, row-major):
+ * [M, C] outputs p_outside, p_above, p_below, r0_mean (Hodges-Lehmann location of the other cells), p_threshold; [M] outputs cells_var, weakest_link. */
+int bgp_fault_eval(bgp_ctx* ctx, const double* r0, const double* r0var, int64_t M, int64_t C, int64_t ld, double band, double threshold,
+                   double* p_outside, double* p_above, double* p_below, double* r0_mean, double* p_threshold, double* cells_var,
+                   double* weakest_link, void* stream);
 
 /* ---- multi-GPU building blocks (block-row-cyclic sharded Cholesky; the NCCL exchange lives in Python/
  * torch.distributed, see battgp_b200/sharded.py) --------------------------------------------------------------

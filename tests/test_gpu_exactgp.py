@@ -145,25 +145,47 @@ def test_large_n_properties(eng):
     assert bool(torch.isfinite(m).all())
 
 
-def test_cell_batch_matches_oracle(eng):
-    """battgp_full.py:41-60,100-120: several cells of one battery, shared buffers, one H2D / one D2H."""
+@pytest.mark.parametrize("concurrent", [False, True])
+def test_cell_batch_matches_oracle(eng, concurrent):
+    """battgp_full.py:41-60,100-120: several cells of one battery.  concurrent=False: one after another with shared buffers, one
+    H2D / one D2H; concurrent=True (the default for the reference's N = 1000 cells): one stream + context per cell, the whole
+    battery captured in a CUDA graph and replayed for the next battery of the same shape."""
     from battgp_b200 import engine as E
     from battgp_b200.batch import CellBatch
     from battgp_b200.synth import synth_field_data
-    sizes = [600, 701, 350]
-    xs, ys, xqs = [], [], []
-    for c, n in enumerate(sizes):
-        x, y = synth_field_data(n, seed=0, cell=c)
-        xs.append(x); ys.append(y); xqs.append(orc.query_grid(x))
-    cb = CellBatch("cuda:0", n_max=800, m_query=300)
-    means, vars_, lmls = cb.run(E.battgp_spec(), 2.33e-6, xs, ys, xqs)
-    assert means.shape == (3, 300) and vars_.shape == (3, 300)
-    for c in range(3):
-        f = orc.fit(orc.battgp_spec(), xs[c], ys[c], 2.33e-6)
-        mr, vr = orc.predict(orc.battgp_spec(), xs[c], f, xqs[c])
-        np.testing.assert_allclose(means[c], mr, rtol=1e-7)
-        np.testing.assert_allclose(vars_[c], vr, rtol=1e-6)
-        assert abs(lmls[c] - f.lml) < 1e-9 * abs(f.lml)
+    sizes = [600, 701, 350, 600]
+    cb = CellBatch("cuda:0", n_max=800, m_query=300, concurrent=concurrent, max_streams=3)
+    assert cb.concurrent == concurrent
+    for battery in range(3):                      # same shapes, new data: batteries 1 and 2 replay the captured graph
+        xs, ys, xqs = [], [], []
+        for c, n in enumerate(sizes):
+            x, y = synth_field_data(n, seed=10 * battery, cell=c)
+            xs.append(x); ys.append(y); xqs.append(orc.query_grid(x))
+        means, vars_, lmls = cb.run(E.battgp_spec(), 2.33e-6, xs, ys, xqs)
+        assert means.shape == (4, 300) and vars_.shape == (4, 300)
+        for c in range(4):
+            f = orc.fit(orc.battgp_spec(), xs[c], ys[c], 2.33e-6)
+            mr, vr = orc.predict(orc.battgp_spec(), xs[c], f, xqs[c])
+            np.testing.assert_allclose(means[c], mr, rtol=1e-7)
+            np.testing.assert_allclose(vars_[c], vr, rtol=1e-6)
+            assert abs(lmls[c] - f.lml) < 1e-9 * abs(f.lml)
+    if concurrent:
+        assert cb.graph_replays == 3 and len(cb._graphs) == 1
+        # a cell that is not positive definite at the first attempt falls back to the jitter-retry path
+        x = np.zeros((40, 4)); x[:, 1] = np.repeat(np.arange(20.0), 2); x[:, 0] = 1.0
+        y = np.arange(40.0)
+        import warnings
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            spec0 = E.KernelSpec([E.Term(E.RBF, [1, 2, 3], 1.0, (1.0, 1.0, 1.0))])
+            cb2 = CellBatch("cuda:0", n_max=64, m_query=5)
+            xq = np.column_stack([np.ones(5), np.arange(5.0), np.zeros(5), np.zeros(5)])
+            m2, v2, l2 = cb2.run(spec0, 0.0, [x], [y], [xq])
+            st = E.fit(spec0, _t(x), _t(y), 0.0)
+            mr, vr = E.predict(st, _t(xq))
+        assert st.jitter > 0
+        np.testing.assert_allclose(m2[0], mr.cpu().numpy(), rtol=1e-9)
+        np.testing.assert_allclose(v2[0], vr.cpu().numpy(), rtol=1e-9)
 
 
 REAL_PATH = __import__("os").path.join(__import__("os").path.dirname(__file__), "golden", "real_field_data.npz")

@@ -101,3 +101,87 @@ def test_sharded_two_ranks_nccl_matches_oracle():
         np.testing.assert_allclose(mean, mr, rtol=1e-7)
         np.testing.assert_allclose(var, vr, rtol=1e-6)
         assert recv > 0
+
+
+def _facade_worker(rank, world, port, q):
+    """Every rank builds the SAME model with MultiDeviceKernel(device_ids=range(world)) -- the reference's only intra-GP
+    multi-device knob (cell_gp.py:38-43) -- and calls it in eval mode; the facade routes it to the sharded engine."""
+    import sys
+    import warnings
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    try:
+        root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+        sys.path.insert(0, os.path.join(root, "tools"))
+        import run_reference_modules as rrm
+        torch.set_default_dtype(torch.float64)
+        g = np.load(os.path.join(root, "tests", "golden", "real_field_data.npz"))
+        x, y, xq = g["b14_c3_x"], g["b14_c3_y"], g["b14_c3_xq"]
+        dev = torch.device("cuda", rank)
+        ref = rrm.find_reference()
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            if ref is not None:                      # the reference's own classes, unmodified
+                rrm.install(ref)
+                from src.batt_models.battcellgp_full import BatteryCellGP_Full
+                cell = BatteryCellGP_Full(x, y, 3, device=dev, n_devices=world, output_device=dev)
+                mean, var = cell.predict(xq)
+                used = "reference BatteryCellGP_Full(n_devices=%d)" % world
+                strat = cell.model.prediction_strategy
+            else:
+                import battgp_b200.shim as shim
+                shim.install(force=True)
+                import gpytorch
+
+                class M(gpytorch.models.ExactGP):
+                    def __init__(self, tx, ty):
+                        super().__init__(tx, ty, gpytorch.likelihoods.GaussianLikelihood(noise_constraint=gpytorch.constraints.Interval(0.0, 1e5)))
+                        self.mean_module = gpytorch.means.ZeroMean()
+                        k = gpytorch.kernels.ScaleKernel(gpytorch.kernels.RBFKernel(ard_num_dims=3, active_dims=[1, 2, 3]))
+                        self.covar_module = gpytorch.kernels.MultiDeviceKernel(k, device_ids=range(world), output_device=dev)
+                        self.to(tx.device)
+
+                    def forward(self, xx):
+                        return gpytorch.distributions.MultivariateNormal(self.mean_module(xx), self.covar_module(xx))
+                m = M(_t(x, dev), _t(y, dev))
+                m.likelihood.noise = torch.tensor([2.33e-6], device=dev)
+                m.covar_module.base_kernel.outputscale = torch.tensor(0.0099, device=dev)
+                m.covar_module.base_kernel.base_kernel.lengthscale = torch.tensor([12.11, 33.75, 45.14], device=dev)
+                m.eval()
+                out = m(_t(xq, dev))
+                mean, var = out.mean.cpu().numpy(), out.variance.cpu().numpy()
+                used = "local ExactGP with MultiDeviceKernel"
+                strat = m.prediction_strategy
+        q.put((rank, used, np.asarray(mean), np.asarray(var), type(strat[1]).__name__))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs two GPUs")
+def test_multi_device_kernel_routes_to_the_sharded_engine():
+    import torch.multiprocessing as mp
+    world = 2
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    ps = [ctx.Process(target=_facade_worker, args=(r, world, port, q)) for r in range(world)]
+    [p.start() for p in ps]
+    res = [q.get(timeout=300) for _ in range(world)]
+    [p.join(timeout=60) for p in ps]
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    g = np.load(os.path.join(root, "tests", "golden", "real_field_data.npz"))
+    for rank, used, mean, var, strat in res:
+        assert strat == "ShardedGP", (used, strat)
+        if used.startswith("reference"):
+            np.testing.assert_allclose(mean, g["b14_c3_mean"], rtol=1e-6)
+            np.testing.assert_allclose(var, g["b14_c3_var"], rtol=1e-4)
+        else:
+            spec = orc.scaled_rbf_spec(3, 0.0099, 1.0)
+            spec.terms[0].dims = [1, 2, 3]; spec.terms[0].lengthscale = (12.11, 33.75, 45.14)
+            f = orc.fit(spec, g["b14_c3_x"], g["b14_c3_y"], 2.33e-6)
+            mr, vr = orc.predict(spec, g["b14_c3_x"], f, g["b14_c3_xq"])
+            np.testing.assert_allclose(mean, mr, rtol=1e-6)
+            np.testing.assert_allclose(var, vr, rtol=1e-4)

@@ -276,7 +276,26 @@ def check_scaled_rbf(dev, emit):
          "tolerance": {"mean_abs": 1e-4, "var_abs": 1e-4, "cov_rel_fro": 1e-4}}
     r["ok"] = bool(r["mean_max_abs"] < 1e-4 and r["var_max_abs"] < 1e-4 and r["full_cov_rel_fro"] < 1e-4)
     emit(r)
-    return r["ok"]
+    ok = r["ok"]
+    # SparseScaledRBFModel (standard_models.py:58-107, SGPR through InducingPointKernel): subset-of-regressors prediction
+    from src.gp.standard_models import SparseScaledRBFModel
+    u = x[rng.choice(200, 25, replace=False)]
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        sgp = SparseScaledRBFModel(torch.tensor(x), torch.tensor(y), torch.tensor(u), 0.05, 1.3, 0.9)
+        ms, vs = sgp.predict(xq)
+    u32 = u.astype(np.float32).astype(np.float64)
+    nz = float(np.float32(0.05))
+    Kuu = orc.cov(spec, u32, u32); Kfu = orc.cov(spec, x32, u32); Ksu = orc.cov(spec, xq32, u32)
+    Qff = Kfu @ np.linalg.solve(Kuu, Kfu.T); Qsf = Ksu @ np.linalg.solve(Kuu, Kfu.T); Qss = Ksu @ np.linalg.solve(Kuu, Ksu.T)
+    G = Qff + nz * np.eye(200)
+    mref = Qsf @ np.linalg.solve(G, y32)
+    vref = np.diag(Qss - Qsf @ np.linalg.solve(G, Qsf.T))
+    r = {"check": "SparseScaledRBFModel.predict (SGPR, standard_models.py:58-107)", "mean_max_abs": float(np.max(np.abs(ms - mref))),
+         "var_max_abs": float(np.max(np.abs(vs - vref))), "tolerance": {"mean_abs": 2e-4, "var_abs": 2e-4}}
+    r["ok"] = bool(r["mean_max_abs"] < 2e-4 and r["var_max_abs"] < 2e-4)
+    emit(r)
+    return bool(ok and r["ok"])
 
 
 # ------------------------------------------------------------------------------------------------------------ (iv)
