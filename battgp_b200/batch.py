@@ -44,6 +44,7 @@ class CellBatch:
         self._slots = []          # concurrent mode: (Engine, stream, K buffer)
         self._graphs = {}         # key -> captured battery
         self.graph_replays = 0
+        self.use_graph = True
 
     def _kview(self, K: torch.Tensor, n: int) -> torch.Tensor:
         """(n + m) x n view of a K buffer with an even leading dimension."""
@@ -168,16 +169,28 @@ class CellBatch:
                 g["enqueue"]()                        # eager once: function attributes, allocator warm-up
             torch.cuda.current_stream(self.device).wait_stream(side)
             torch.cuda.synchronize(self.device)
-            graph = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(graph):
-                g["enqueue"]()
-            g["graph"] = graph
+            g["graph"] = None
+            if self.use_graph:
+                try:
+                    graph = torch.cuda.CUDAGraph()
+                    with torch.cuda.graph(graph):
+                        g["enqueue"]()
+                    g["graph"] = graph
+                except Exception as e:            # capture not possible here: stay concurrent, launch eagerly
+                    import warnings
+                    warnings.warn(f"CellBatch: CUDA graph capture failed ({type(e).__name__}: {e}); running the cells concurrently "
+                                  "without a graph", RuntimeWarning)
+                    self.use_graph = False
+                    torch.cuda.synchronize(self.device)
             if len(self._graphs) >= 8:
                 self._graphs.pop(next(iter(self._graphs)))
             self._graphs[key] = g
         self._fill(g["host_in"], g["slots"], xs, ys, xqs, D)
-        g["graph"].replay()
-        self.graph_replays += 1
+        if g["graph"] is not None:
+            g["graph"].replay()
+            self.graph_replays += 1
+        else:
+            g["enqueue"]()
         torch.cuda.current_stream(self.device).synchronize()
         res = g["host_out"].numpy()
         means = res[:C * m].reshape(C, m).copy()

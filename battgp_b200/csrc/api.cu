@@ -207,8 +207,14 @@ static int potrf_driver(Ctx* ctx, double* A, int64_t n, int64_t mx, int64_t lda,
                     }
                     BGP_CUDA_OK(cudaEventRecord(ctx->prof_ev[2 * ctx->prof_used], mainst));
                 }
-                if ((rc = oz_gemm(ctx, ozbuf[k & 1], below, wnext, ozbuf[k & 1], below, wnext, R - t0, n - t0, nbk, -1.0,
-                                  A + t0 * lda + t0, lda, 1, 0, 0, mainst, ctx->oz_tpc))) return rc;
+                // tail panels: the panel chain is what is exposed there, so the (short) trailing update runs as one persistent
+                // CTA per SM on all but oz_reserve SMs and the high-priority panel kernels start without waiting for a CTA to retire
+                const bool tail = ctx->sched_tail > 0 && (R - k0) < ctx->sched_tail;
+                ctx->oz_reserve_now = tail ? ctx->oz_reserve : 0;
+                rc = oz_gemm(ctx, ozbuf[k & 1], below, wnext, ozbuf[k & 1], below, wnext, R - t0, n - t0, nbk, -1.0,
+                             A + t0 * lda + t0, lda, 1, 0, 0, mainst, tail ? 0 : ctx->oz_tpc);
+                ctx->oz_reserve_now = 0;
+                if (rc) return rc;
                 if (prof) {
                     BGP_CUDA_OK(cudaEventRecord(ctx->prof_ev[2 * ctx->prof_used + 1], mainst));
                     const double c = (double)(n - t0);          // lower triangle of the square part + the full extra rows
@@ -335,10 +341,13 @@ int bgp_ctx_set(bgp_ctx* p, const char* key, int value) {
         if (!strcmp(key, "sched_t4096")) { c->sched_t4096 = value; return 0; }
         if (!strcmp(key, "sched_w0")) { c->sched_w0 = value; return 0; }
         if (!strcmp(key, "sched_w1")) { c->sched_w1 = value; return 0; }
+        if (!strcmp(key, "sched_tail")) { c->sched_tail = value; return 0; }
         return BGP_E_ARG;
     }
     if (!strcmp(key, "ozaki")) { c->ozaki = value ? 1 : 0; return 0; }
     if (!strcmp(key, "oz_cluster")) { if (value != 1 && value != 2 && value != 4) return BGP_E_ARG; c->oz_cluster = value; return 0; }
+    if (!strcmp(key, "oz_l2hint")) { if (value < 0 || value > 3) return BGP_E_ARG; c->oz_l2hint = value; return 0; }
+    if (!strcmp(key, "oz_reserve")) { if (value < 0 || value > 128) return BGP_E_ARG; c->oz_reserve = value; return 0; }
     if (!strcmp(key, "oz_group")) { if (value < 1 || value > 1024) return BGP_E_ARG; c->oz_group = value; return 0; }
     if (!strcmp(key, "oz_tpc_gemm")) { if (value < 0 || value > 4096) return BGP_E_ARG; c->oz_tpc_gemm = value; return 0; }
     if (!strcmp(key, "oz_tpc")) { if (value < 0 || value > 4096) return BGP_E_ARG; c->oz_tpc = value; return 0; }

@@ -38,7 +38,11 @@ struct Ctx {
     int64_t ws_bytes = 0;
     void* ws_trsm = nullptr;                // tail of ws used by the TRSM updates (set by bgp_potrf for its panels)
     int64_t ws_trsm_bytes = 0;
+    int oz_reserve = 0;                     // SMs left free by the persistent trailing update of the tail panels (sched_tail)
+    int sched_tail = 0;                     // rows still to factorise below which the trailing updates run persistent on nsm - oz_reserve SMs (0 = never)
+    int oz_reserve_now = 0;                 // set by bgp_potrf around such a launch
     int oz_tpc_gemm = 0;                    // tiles per CTA of stand-alone bgp_oz_gemm calls (0 = fully persistent)
+    int oz_l2hint = 0;                      // L2 cache-policy variant of the int8 kernel (ozaki.cu OzArgs::l2hint)
     int oz_group = 8;                       // tile rows per raster group of the int8 kernel
     long long* oz_dbg = nullptr;            // diagnostics: clock64 timeline of CTA 0 (bgp_debug_oz_timeline)
     int oz_dbg_cap = 0;

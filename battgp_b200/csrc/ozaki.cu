@@ -133,6 +133,17 @@ __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                  ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
 }
+// operand planes are re-read by the other CTAs of the raster group and by the next raster step: keep them in L2 ahead of
+// the streaming C traffic
+__device__ __forceinline__ uint64_t l2_policy_evict_last() {
+    uint64_t p;
+    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
+    return p;
+}
+__device__ __forceinline__ void bulk_g2s_hint(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar, uint64_t pol) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;"
+                 ::"r"(dst), "l"(src), "r"(bytes), "r"(bar), "l"(pol) : "memory");
+}
 __device__ __forceinline__ void bulk_g2s_mc(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar, uint16_t mask) {
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1], %2, [%3], %4;"
                  ::"r"(dst), "l"(src), "r"(bytes), "r"(bar), "h"(mask) : "memory");
@@ -199,6 +210,7 @@ struct OzArgs {
     int tri; int64_t roff, coff;
     int debug_noload;      // experiment: only the first OZ_STAGES k-blocks are really loaded
     int group;             // raster: tile rows per group (oz_decode)
+    int l2hint;            // 0: default L2 policy; 1: operand loads evict_last; 2: + streaming C accesses; 3: as 2, no C prefetch
     int64_t brb_max;       // last valid 128-row block of B (cluster tiles past N read a valid block; stores are masked)
     long long* dbg;        // diagnostics: per-tile clock64 stamps of CTA 0 (bgp_debug_oz_timeline), 16 slots per tile
     int dbg_cap;
@@ -283,6 +295,7 @@ __global__ void __launch_bounds__(192, 1) oz_mma_kernel(OzArgs g, int tiles_m, i
     // issues): operands then live in uniform registers and no per-lane "waterfall" code is generated around UTCIMMA.
     if (warp == 0) {
         uint32_t it = 0, tile_it = 0;                           // k-block counter across tiles
+        const uint64_t pol = l2_policy_evict_last();
         for (int pid = pid_begin; pid < pid_end; pid += pid_step) {
             int m0, n0;
             if (!oz_decode<CS>(g, pid, tiles_m, tiles_ng, (int)crank, m0, n0)) continue;
@@ -301,16 +314,23 @@ __global__ void __launch_bounds__(192, 1) oz_mma_kernel(OzArgs g, int tiles_m, i
                         mbar_expect_tx(full0 + 8 * st, OZ_A_STAGE + OZ_B_STAGE);
                         const int8_t* asrc = g.sa + ((int64_t)kb * g.nrb_a + arb) * OZ_S * OZ_SLICE_TILE;
                         if (CS == 1) {
-                            bulk_g2s(smem_u32(sA + st * OZ_A_STAGE), asrc, OZ_A_STAGE, full0 + 8 * st);
+                            if (g.l2hint) bulk_g2s_hint(smem_u32(sA + st * OZ_A_STAGE), asrc, OZ_A_STAGE, full0 + 8 * st, pol);
+                            else bulk_g2s(smem_u32(sA + st * OZ_A_STAGE), asrc, OZ_A_STAGE, full0 + 8 * st);
                         } else {
                             constexpr int APART = OZ_A_STAGE / CS;  // this CTA's share of the A stage, delivered to all CS CTAs
                             bulk_g2s_mc(smem_u32(sA + st * OZ_A_STAGE + crank * APART), asrc + (int64_t)crank * APART, APART,
                                         full0 + 8 * st, (uint16_t)((1u << CS) - 1));
                         }
                         const int8_t* bsrc = g.sb + ((int64_t)kb * g.nrb_b + brb) * OZ_S * OZ_SLICE_TILE + bhalf * 4096;
+                        if (g.l2hint) {
 #pragma unroll
-                        for (int s = 0; s < OZ_S; s++)
-                            bulk_g2s(smem_u32(sB + st * OZ_B_STAGE + s * 4096), bsrc + (int64_t)s * OZ_SLICE_TILE, 4096, full0 + 8 * st);
+                            for (int s = 0; s < OZ_S; s++)
+                                bulk_g2s_hint(smem_u32(sB + st * OZ_B_STAGE + s * 4096), bsrc + (int64_t)s * OZ_SLICE_TILE, 4096, full0 + 8 * st, pol);
+                        } else {
+#pragma unroll
+                            for (int s = 0; s < OZ_S; s++)
+                                bulk_g2s(smem_u32(sB + st * OZ_B_STAGE + s * 4096), bsrc + (int64_t)s * OZ_SLICE_TILE, 4096, full0 + 8 * st);
+                        }
                     }
                 }
                 __syncwarp();
@@ -377,7 +397,7 @@ __global__ void __launch_bounds__(192, 1) oz_mma_kernel(OzArgs g, int tiles_m, i
             const int row_l = q * 32 + lane;
             const double sa = (m0 + row_l < g.M) ? g.alpha * g.exa[g.arow0 + m0 + row_l] * (1.0 / 16384.0) : 0.0;
             // pull this warp's 32 x 64 block of C towards L2 while the MMAs of the tile run (lane = row, 4 lines of 128 B)
-            if (m0 + row_l < g.M) {
+            if (m0 + row_l < g.M && g.l2hint != 3) {
                 const double* crow = g.C + (int64_t)(m0 + row_l) * g.ldc + n0;
 #pragma unroll
                 for (int i = 0; i < 4; i++)
@@ -433,10 +453,17 @@ __global__ void __launch_bounds__(192, 1) oz_mma_kernel(OzArgs g, int tiles_m, i
                 double* cp = g.C + (int64_t)rbase * g.ldc + col;
                 double cold[32];
                 if (__all_sync(0xffffffffu, r_lo == 0 && r_end == 32)) {                // interior tile: no predicates at all
+                    if (g.l2hint >= 2) {                                                 // C is touched once: streaming (evict-first) accesses
 #pragma unroll
-                    for (int r = 0; r < 32; r++) cold[r] = cp[(int64_t)r * g.ldc];
+                        for (int r = 0; r < 32; r++) cold[r] = __ldcs(cp + (int64_t)r * g.ldc);
 #pragma unroll
-                    for (int r = 0; r < 32; r++) cp[(int64_t)r * g.ldc] = cold[r] + tbuf[r * 33 + lane] * sb;
+                        for (int r = 0; r < 32; r++) __stcs(cp + (int64_t)r * g.ldc, cold[r] + tbuf[r * 33 + lane] * sb);
+                    } else {
+#pragma unroll
+                        for (int r = 0; r < 32; r++) cold[r] = cp[(int64_t)r * g.ldc];
+#pragma unroll
+                        for (int r = 0; r < 32; r++) cp[(int64_t)r * g.ldc] = cold[r] + tbuf[r * 33 + lane] * sb;
+                    }
                 } else {
 #pragma unroll
                     for (int r = 0; r < 32; r++) cold[r] = (r >= r_lo && r < r_end) ? cp[(int64_t)r * g.ldc] : 0.0;
@@ -488,6 +515,7 @@ int oz_gemm(Ctx* ctx, const void* bufA, int64_t rowsA_total, int64_t arow0, cons
     g.C = C; g.ldc = ldc; g.M = (int)M; g.N = (int)N; g.K = (int)K; g.alpha = alpha; g.tri = tri; g.roff = roff; g.coff = coff;
     g.debug_noload = (ctx->gemm_cfg == 7) ? 1 : 0;
     g.group = ctx->oz_group > 0 ? ctx->oz_group : 8;
+    g.l2hint = ctx->oz_l2hint;
     g.brb_max = g.nrb_b - 1;
     g.dbg = ctx->oz_dbg; g.dbg_cap = ctx->oz_dbg_cap;
     const int tiles_m = (int)((M + OZ_BM - 1) / OZ_BM), tiles_n = (int)((N + OZ_BN - 1) / OZ_BN);
@@ -528,7 +556,9 @@ int oz_gemm(Ctx* ctx, const void* bufA, int64_t rowsA_total, int64_t arow0, cons
         return 0;
     }
     const int total = tiles_m * tiles_n;
-    const int grid = tpc > 0 ? (total + tpc - 1) / tpc : (total < nsm ? total : nsm);
+    int nfree = nsm - (tpc == 0 ? ctx->oz_reserve_now : 0);
+    if (nfree < 1) nfree = 1;
+    const int grid = tpc > 0 ? (total + tpc - 1) / tpc : (total < nfree ? total : nfree);
     oz_mma_kernel<1><<<grid, 192, SMEM, st>>>(g, tiles_m, tiles_n, tpc);
     BGP_LAUNCH_OK(ctx);
     return 0;

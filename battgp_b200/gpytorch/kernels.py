@@ -255,6 +255,8 @@ def dense_cov(kernel: "Kernel", x1: torch.Tensor, x2: torch.Tensor) -> torch.Ten
     b = bind_spec(kernel, x1.shape[-1])
     if b is None:
         xs1, xs2 = kernel._select(x1), kernel._select(x2)
+        if isinstance(kernel, InducingPointKernel):     # fp64 all the way into the exact path (callers widen anyway)
+            return kernel._forward64(xs1, xs2)
         return kernel.forward(xs1, xs2)
     dev = compute_device(x1)
     out = E.get_engine(dev).cov_build(b.to_spec(), _stage(x1, dev), _stage(x2, dev))
@@ -300,6 +302,8 @@ def _torch_base(k: "Kernel", a: torch.Tensor, b: torch.Tensor) -> torch.Tensor:
 def dense_cov_diag(kernel: "Kernel", x: torch.Tensor) -> torch.Tensor:
     b = bind_spec(kernel, x.shape[-1])
     if b is None:
+        if isinstance(kernel, InducingPointKernel):
+            return kernel._forward64(kernel._select(x), kernel._select(x), diag=True)
         return kernel(x, x, diag=True)
     dev = compute_device(x)
     return E.get_engine(dev).cov_diag(b.to_spec(), _stage(x, dev)).to(device=x.device, dtype=x.dtype)
@@ -521,17 +525,23 @@ class InducingPointKernel(Kernel):
             inducing_points = inducing_points.unsqueeze(-1)
         self.register_parameter("inducing_points", torch.nn.Parameter(inducing_points))
 
-    def _root(self, x: torch.Tensor, Luu: torch.Tensor, dinv: torch.Tensor, dev) -> torch.Tensor:
+    def _root(self, x: torch.Tensor, u: torch.Tensor, Luu: torch.Tensor, dinv: torch.Tensor, dev) -> torch.Tensor:
         """A = K_xu L_uu^-T  [n, m], fp64 on the compute device."""
         eng = E.get_engine(dev)
-        Kxu = E.alloc_matrix(x.shape[0], self.inducing_points.shape[0], dev)
-        Kxu.copy_(dense_cov(self.base_kernel, x, self.inducing_points.to(x)).to(device=dev, dtype=torch.float64))
+        Kxu = E.alloc_matrix(x.shape[0], u.shape[0], dev)
+        Kxu.copy_(dense_cov(self.base_kernel, x, u).to(device=dev, dtype=torch.float64))
         return eng.trsm_rlt(Luu, dinv, Kxu)
 
-    def forward(self, x1, x2, diag=False, **params):
+    def _forward64(self, x1, x2, diag=False):
+        """k_Q(x1, x2) in fp64 on the compute device.  fp32 inputs (standard_models.py:66-67) are widened FIRST, so neither K_xu
+        nor Q is ever rounded to fp32 on its way into the exact path (cond(Q + sigma^2 I) ~ 1e4 would turn that rounding into
+        1e-3 relative errors of the posterior mean)."""
         dev = compute_device(x1)
         eng = E.get_engine(dev)
-        u = self.inducing_points.detach()
+        same = x1 is x2 or (x1.shape == x2.shape and torch.equal(x1, x2))
+        x1 = x1.detach().to(torch.float64)
+        x2 = x1 if same else x2.detach().to(torch.float64)
+        u = self.inducing_points.detach().to(device=x1.device, dtype=torch.float64)
         m = u.shape[0]
         Kuu = E.alloc_matrix(m, m, dev)
         Kuu.copy_(dense_cov(self.base_kernel, u, u).to(device=dev, dtype=torch.float64))
@@ -546,9 +556,8 @@ class InducingPointKernel(Kernel):
             if attempt == len(E.JITTERS_F64):
                 raise E.NotPSDError("inducing-point covariance K_uu is not positive definite")
             jitter = E.JITTERS_F64[attempt]
-        same = x1 is x2 or (x1.shape == x2.shape and torch.equal(x1, x2))
-        A1 = self._root(x1, L, dinv, dev)
-        A2 = A1 if same else self._root(x2, L, dinv, dev)
+        A1 = self._root(x1, u, L, dinv, dev)
+        A2 = A1 if same else self._root(x2, u, L, dinv, dev)
         if diag:
             out = torch.empty(x1.shape[0], dtype=torch.float64, device=dev)
             if same:
@@ -557,11 +566,21 @@ class InducingPointKernel(Kernel):
                 out = (A1 * A2).sum(-1)
             if self.training and same:
                 out = torch.maximum(out, dense_cov_diag(self.base_kernel, x1).to(device=dev, dtype=torch.float64))
-            return out.to(device=x1.device, dtype=x1.dtype)
+            return out
         Q = E.alloc_matrix(x1.shape[0], x2.shape[0], dev)
         eng.gemm_nt(A1, A2, Q, alpha=1.0, beta=0.0)
         if self.training and same:
             kd = dense_cov_diag(self.base_kernel, x1).to(device=dev, dtype=torch.float64)
             corr = (kd - Q.diagonal()).clamp_min(0.0)
             Q.diagonal().add_(corr)
-        return Q.to(device=x1.device, dtype=x1.dtype)
+        return Q
+
+    def forward(self, x1, x2, diag=False, **params):
+        return self._forward64(x1, x2, diag=diag).to(device=x1.device, dtype=x1.dtype)
+
+
+# gpytorch/kernels/kernel.py is a module in GPyTorch: `gpytorch.kernels.kernel` appears as a type annotation in the reference's
+# tests/gp/test_spatiotemporal_gp.py:89
+import sys as _sys
+
+kernel = _sys.modules[__name__]

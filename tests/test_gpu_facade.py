@@ -301,3 +301,45 @@ def test_constraint_errors_and_set_order(gpytorch):
     lik.noise_covar.raw_noise_constraint = gpytorch.constraints.Interval(0.0, 1e5)
     lik.noise = 2.33e-6
     assert abs(float(lik.noise) - 2.33e-6) < 1e-9
+
+
+def test_inducing_point_kernel_sgpr_prediction(gpytorch):
+    """standard_models.py:58-107 (SparseScaledRBFModel): ExactGP over InducingPointKernel = subset-of-regressors prediction,
+    fp32 tensors in and out, checked against the closed form evaluated with numpy in fp64."""
+    rng = np.random.default_rng(11)
+    n, m, q = 300, 30, 25
+    x = rng.normal(size=(n, 2)).astype(np.float32); y = (np.sin(2 * x[:, 0]) + 0.1 * rng.normal(size=n)).astype(np.float32)
+    u = x[rng.choice(n, m, replace=False)]; xq = rng.normal(size=(q, 2)).astype(np.float32)
+
+    class Sparse(gpytorch.models.ExactGP):
+        def __init__(self, tx, ty, ind):
+            lik = gpytorch.likelihoods.GaussianLikelihood()
+            super().__init__(tx, ty, lik)
+            self.mean_module = gpytorch.means.ZeroMean()
+            self.base_covar_module = gpytorch.kernels.ScaleKernel(gpytorch.kernels.RBFKernel())
+            self.likelihood.noise = 0.05
+            self.base_covar_module.outputscale = 1.3
+            self.base_covar_module.base_kernel.lengthscale = 0.9
+            self.covar_module = gpytorch.kernels.InducingPointKernel(self.base_covar_module, inducing_points=ind, likelihood=lik)
+            self.eval()
+
+        def forward(self, xx):
+            return gpytorch.distributions.MultivariateNormal(self.mean_module(xx), self.covar_module(xx))
+
+    gp = Sparse(torch.tensor(x), torch.tensor(y), torch.tensor(u))
+    with torch.no_grad(), gpytorch.settings.fast_pred_var(), warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        out = gp(torch.tensor(xq))
+    mean = out.mean.numpy().astype(np.float64)
+    var = np.diag(out._covar.detach().cpu().numpy()).astype(np.float64)
+    assert out.mean.dtype == torch.float32
+    spec = orc.scaled_rbf_spec(2, float(np.float32(1.3)), float(np.float32(0.9)))
+    x64, u64, q64, y64 = (a.astype(np.float64) for a in (x, u, xq, y))
+    Kuu = orc.cov(spec, u64, u64); Kfu = orc.cov(spec, x64, u64); Ksu = orc.cov(spec, q64, u64)
+    W = np.linalg.solve(Kuu, Kfu.T)
+    G_ = Kfu @ W + float(np.float32(0.05)) * np.eye(n)
+    Qsf = Ksu @ W
+    mref = Qsf @ np.linalg.solve(G_, y64)
+    vref = np.diag(Ksu @ np.linalg.solve(Kuu, Ksu.T) - Qsf @ np.linalg.solve(G_, Qsf.T))
+    np.testing.assert_allclose(mean, mref, atol=2e-4)
+    np.testing.assert_allclose(var, vref, atol=2e-4)

@@ -378,3 +378,33 @@ if "oz2" in what:
                           "ms_dmma": round(ms0, 3), "tflops_equiv_modular": round(2 * M * N * K / ms2 * 1e-9, 2),
                           "tflops_equiv_digitplanes": round(2 * M * N * K / ms1 * 1e-9, 2), "rel_diff_vs_dmma": rel}), flush=True)
         del A, B, C1, C2, C3
+
+if "sched2" in what:
+    # round 2: first-panel width, tail policy (persistent trailing updates on nsm - reserve SMs below `sched_tail` rows), tiles per CTA
+    spec = E.battgp_spec()
+    DEF = {"sched_t1024": 9000, "sched_t2048": 17000, "sched_t4096": 0, "sched_w0": 0, "sched_w1": 0, "sched_tail": 0, "oz_reserve": 0, "oz_tpc": 2}
+    def run(n, xd, K, cfg, reps=2):
+        for k, v in DEF.items(): eng.set(k, cfg.get(k, v))
+        eng.set("nb", cfg.get("nb", 0)); eng.set("ozaki", 1)
+        best = 1e30
+        for r in range(reps):
+            eng.cov_build(spec, xd, noise=2.33e-6, symmetric=True, out=K)
+            torch.cuda.synchronize()
+            e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+            e0.record(); info, ld, dinv = eng.potrf(K); e1.record(); torch.cuda.synchronize()
+            best = min(best, e0.elapsed_time(e1))
+        print(json.dumps({"op": "potrf_sched2", "n": n, "cfg": cfg, "info": info, "logdet": ld, "ms": round(best, 3)}), flush=True)
+    cfgs = [{}, {"sched_w0": 1024}, {"sched_w0": 512}, {"sched_w0": 1024, "sched_w1": 1024},
+            {"sched_tail": 16000, "oz_reserve": 8}, {"sched_tail": 16000, "oz_reserve": 16}, {"sched_tail": 16000, "oz_reserve": 32},
+            {"sched_tail": 24000, "oz_reserve": 16}, {"sched_tail": 10000, "oz_reserve": 16}, {"sched_tail": 10000, "oz_reserve": 32},
+            {"sched_tail": 50000, "oz_reserve": 8}, {"sched_tail": 50000, "oz_reserve": 16},
+            {"sched_t2048": 12000}, {"sched_t2048": 22000}, {"sched_t1024": 5000}, {"sched_t1024": 12000},
+            {"oz_tpc": 4}, {"oz_tpc": 3}, {"sched_t4096": 30000}, {"sched_w0": 1024, "sched_tail": 16000, "oz_reserve": 16}]
+    for n in (40000, 16384):
+        x, y = synth_field_data(n, 0)
+        xd = torch.tensor(x, device=dev)
+        K = E.alloc_matrix(n, n, dev)
+        for cfg in cfgs: run(n, xd, K, cfg)
+        del K
+    for k, v in DEF.items(): eng.set(k, v)
+    eng.set("nb", 0)

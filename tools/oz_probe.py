@@ -89,11 +89,25 @@ elif what == "raster":
                                   "tflops_equiv": round(n * n * k / ms * 1e-9, 2)}), flush=True)
         eng.set("oz_group", 8)
         del A, Cm, buf
+elif what == "l2hint":
+    n = 16384
+    eng.set("oz_cluster", 1)
+    for k in (2048, 1024):
+        A, Cm, buf = syrk_setup(n, k)
+        for hint in (0, 1, 2, 3):
+            eng.set("oz_l2hint", hint)
+            ms = ev(lambda: syrk(buf, n, k, Cm), reps=5)
+            print(json.dumps({"op": "oz_syrk_l2hint", "n": n, "K": k, "l2hint": hint, "ms": round(ms, 4),
+                              "tflops_equiv": round(n * n * k / ms * 1e-9, 2)}), flush=True)
+        eng.set("oz_l2hint", 0)
+        del A, Cm, buf
 elif what == "one":
     grp, k = int(sys.argv[2]), int(sys.argv[3])
     n = 16384
     eng.set("oz_cluster", 1)
     eng.set("oz_group", grp)
+    if len(sys.argv) > 4:
+        eng.set("oz_l2hint", int(sys.argv[4]))
     A, Cm, buf = syrk_setup(n, k)
     for _ in range(3):
         syrk(buf, n, k, Cm)
