@@ -64,6 +64,30 @@ def test_trsv_gemv_t_rowsumsq_blocks(eng):
     np.testing.assert_allclose(acc.cpu().numpy(), 1 + (M ** 2).sum(1), rtol=1e-13)
 
 
+def _collect(q, ps, n, timeout=300.0):
+    """n results from the workers' queue; fails as soon as a worker has died instead of waiting out the timeout."""
+    import queue as _queue
+    import time as _time
+    res, t0 = [], _time.monotonic()
+    while len(res) < n:
+        try:
+            res.append(q.get(timeout=2.0))
+        except _queue.Empty:
+            dead = [p.exitcode for p in ps if p.exitcode not in (None, 0)]
+            if dead:
+                for p in ps:
+                    if p.is_alive():
+                        p.terminate()
+                pytest.fail(f"worker process exited with {dead} before delivering its result")
+            if _time.monotonic() - t0 > timeout:
+                for p in ps:
+                    if p.is_alive():
+                        p.terminate()
+                pytest.fail("timed out waiting for the worker processes")
+    return res
+
+
+
 def _nccl_worker(rank, world, port, n, nb, q):
     import torch.distributed as dist
     os.environ["MASTER_ADDR"] = "127.0.0.1"
@@ -91,7 +115,7 @@ def test_sharded_two_ranks_nccl_matches_oracle():
     q = ctx.Queue()
     ps = [ctx.Process(target=_nccl_worker, args=(r, world, port, n, nb, q)) for r in range(world)]
     [p.start() for p in ps]
-    res = [q.get(timeout=300) for _ in range(world)]
+    res = _collect(q, ps, world)
     [p.join(timeout=60) for p in ps]
     x, y = orc.synth_field_data(n, seed=5)
     f = orc.fit(orc.battgp_spec(), x, y, 2.33e-6)
@@ -169,7 +193,7 @@ def test_multi_device_kernel_routes_to_the_sharded_engine():
     q = ctx.Queue()
     ps = [ctx.Process(target=_facade_worker, args=(r, world, port, q)) for r in range(world)]
     [p.start() for p in ps]
-    res = [q.get(timeout=300) for _ in range(world)]
+    res = _collect(q, ps, world)
     [p.join(timeout=60) for p in ps]
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     g = np.load(os.path.join(root, "tests", "golden", "real_field_data.npz"))

@@ -408,3 +408,34 @@ if "sched2" in what:
         del K
     for k, v in DEF.items(): eng.set(k, v)
     eng.set("nb", 0)
+if "potrf2" in what:
+    # round 2: default schedule at the sizes of the small-N / mid-N targets, A-collector on/off, cuSOLVER (torch) beside it
+    spec = E.battgp_spec()
+    eng.set("nb", 0); eng.set("lookahead", 1)
+    for n in (1024, 2048, 4096, 8192, 16384, 40000):
+        x, y = synth_field_data(n, 0)
+        xd = torch.tensor(x, device=dev)
+        K = E.alloc_matrix(n, n, dev)
+        row = {"op": "potrf2", "n": n}
+        for coll in (1, 0):
+            eng.set("oz_collector", coll)
+            best = 1e30
+            for r in range(4 if n <= 16384 else 2):
+                eng.cov_build(spec, xd, noise=2.33e-6, symmetric=True, out=K)
+                torch.cuda.synchronize()
+                e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+                e0.record(); info, ld, dinv = eng.potrf(K); e1.record(); torch.cuda.synchronize()
+                best = min(best, e0.elapsed_time(e1))
+            row[f"ms_collector{coll}"] = round(best, 3); row["info"] = info; row[f"logdet{coll}"] = ld
+        eng.set("oz_collector", 0)
+        row["tflops_equiv"] = round(n ** 3 / 3 / row["ms_collector1"] * 1e-9, 2)
+        if n <= 16384:
+            eng.cov_build(spec, xd, noise=2.33e-6, symmetric=True, out=K)
+            Kc = K[:, :n].clone()
+            t_copy = ev(lambda: Kc.copy_(K[:, :n]), reps=3)
+            t_both = ev(lambda: torch.linalg.cholesky_ex(Kc.copy_(K[:, :n])), reps=3)
+            row["cusolver_potrf_ms"] = round(t_both - t_copy, 3)
+            del Kc
+        print(json.dumps(row), flush=True)
+        del K
+        torch.cuda.empty_cache()

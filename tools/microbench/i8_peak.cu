@@ -50,7 +50,7 @@ __global__ void __launch_bounds__(128, 1) i8_peak_kernel(int mode, int iters, un
     uint8_t* sA = smem;
     uint8_t* sB = smem + A_BYTES;
     uint64_t* bar = reinterpret_cast<uint64_t*>(sB + B_BYTES);
-    uint32_t* slot = reinterpret_cast<uint32_t*>(bar + 2);
+    uint32_t* slot = reinterpret_cast<uint32_t*>(bar + 10);
     uint32_t x = seed ^ (blockIdx.x * 2654435761u) ^ (threadIdx.x * 40503u);
     for (int i = threadIdx.x; i < (A_BYTES + B_BYTES) / 4; i += blockDim.x) {
         x = x * 1664525u + 1013904223u;
@@ -61,7 +61,7 @@ __global__ void __launch_bounds__(128, 1) i8_peak_kernel(int mode, int iters, un
         reinterpret_cast<uint32_t*>(smem)[i] = w;
     }
     const int warp = threadIdx.x >> 5;
-    if (threadIdx.x == 0) { mbar_init(smem_u32(bar), 1); asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+    if (threadIdx.x == 0) { for (int i = 0; i < 10; i++) mbar_init(smem_u32(bar + i), 1); asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
     if (warp == 0) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(slot)), "r"(512) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
@@ -86,6 +86,25 @@ __global__ void __launch_bounds__(128, 1) i8_peak_kernel(int mode, int iters, un
                     const uint64_t da = da0 + (uint64_t)((((u & 7) * 8192) + ((u >> 3) & 1) * 32) >> 4);
                     mma_i8(tmem + (uint32_t)((u & 1) * 256), da, db0 + (uint64_t)((((u >> 1) & 1) * 32) >> 4), idesc, it > 0 || u > 1);
                 }
+            } else if (mode >= 4) {
+                // the 7-plane schedule of csrc/ozaki.cu (28 plane pairs, s + t <= 6).  mode 4: windows of 4 B planes + the rest
+                // (N = 256+192, 256+128, 256+64, 256, 192, 128, 64); mode 5: balanced windows (256+192, 192+192, 192+128, 256, 192, 128, 64)
+#pragma unroll
+                for (int ks = 0; ks < 2; ks++)
+#pragma unroll
+                    for (int s = 0; s < 7; s++) {
+                        const int cnt = 7 - s;
+                        const int first = (mode != 5) ? (cnt < 4 ? cnt : 4) : (cnt == 7 ? 4 : (cnt >= 5 ? 3 : cnt));
+#pragma unroll
+                        for (int w = 0; w < 2; w++) {
+                            const int t = w == 0 ? 0 : first;
+                            const int nt = w == 0 ? first : cnt - first;
+                            if (nt > 0)
+                                mma_i8(tmem + (uint32_t)(s + t) * 64, da0 + (uint64_t)((s * 8192 + ks * 32) >> 4),
+                                       db0 + (uint64_t)((t * 4096 + ks * 32) >> 4), idesc0 | ((uint32_t)((nt * 64) >> 3) << 17),
+                                       (it > 0 || ks > 0 || s > 0) ? 1u : 0u);
+                        }
+                    }
             } else {
 #pragma unroll
                 for (int ks = 0; ks < 2; ks++)
@@ -98,6 +117,12 @@ __global__ void __launch_bounds__(128, 1) i8_peak_kernel(int mode, int iters, un
                                    db0 + (uint64_t)((t * 4096 + ks * 32) >> 4), idesc0 | ((uint32_t)((nt * 64) >> 3) << 17),
                                    (it > 0 || ks > 0 || s > 0) ? 1u : 0u);
                         }
+            }
+            if (mode == 6) commit(smem_u32(bar + 1));          // like the kernel: one commit per k-block (the barrier is never waited on)
+            if (mode >= 7) {                                   // commit per k-block AND wait until k-block it - D has completed
+                const int D = mode - 6;                        // (what a D-stage operand ring imposes on the issuing thread)
+                if (it >= D) mbar_wait(smem_u32(bar + 2 + (it % D)), ((it / D) - 1) & 1);     // one phase in flight per barrier
+                commit(smem_u32(bar + 2 + (it % D)));
             }
             if ((it & 7) == 7 || it == iters - 1) {          // bound the queue: wait for everything issued so far
                 commit(b);
@@ -120,11 +145,14 @@ int main(int argc, char** argv) {
     unsigned long long* cyc; cudaMalloc(&cyc, sizeof(unsigned long long) * sms);
     unsigned long long* h = (unsigned long long*)malloc(sizeof(unsigned long long) * sms);
     const double secs = argc > 1 ? atof(argv[1]) : 1.0;     // sustained window per mode (power cap sets the clock)
-    const char* names[4] = {"N256", "N128", "N64", "ozaki_wide_n_schedule"};
-    for (int mode = 0; mode < 4; mode++) {
+    const char* names[13] = {"N256", "N128", "N64", "ozaki_wide_n_schedule_8planes_36pairs", "ozaki_7planes_28pairs_windows_4+rest",
+                            "ozaki_7planes_28pairs_balanced_windows", "ozaki_7planes_commit_per_kblock", "ozaki_7planes_commit_wait_kblock-1", "ozaki_7planes_commit_wait_kblock-2",
+                            "ozaki_7planes_commit_wait_kblock-3", "ozaki_7planes_commit_wait_kblock-4", "ozaki_7planes_commit_wait_kblock-5", "ozaki_7planes_commit_wait_kblock-6"};
+    const int first_mode = argc > 2 ? atoi(argv[2]) : 0;
+    for (int mode = first_mode; mode < 13; mode++) {
         // MACs per loop iteration and CTA
         const double macs_it = mode == 0 ? 16.0 * 128 * 256 * 32 : mode == 1 ? 16.0 * 128 * 128 * 32 : mode == 2 ? 16.0 * 128 * 64 * 32
-                                                                                                                  : 2.0 * 36 * 128 * 64 * 32;
+                               : mode == 3 ? 2.0 * 36 * 128 * 64 * 32 : 2.0 * 28 * 128 * 64 * 32;
         int iters = 2000;
         cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
         i8_peak_kernel<<<sms, 128, smem>>>(mode, iters, cyc, 1u);

@@ -66,6 +66,7 @@ if what == "timeline":
                          "mma_first_full_wait": int(t[i, 2] - t[i, 1]), "mma_issue_loop": int(t[i, 3] - t[i, 1]),
                          "epi_prefetch_to_tfull": int(t[i, 5] - t[i, 4]), "epi_drain": int(t[i, 6] - t[i, 5]),
                          "epi_store_after_release": int(t[i, 7] - t[i, 6]),
+                         "epi_h0_loads": int(t[i, 10] - t[i, 6]), "epi_h0_stores": int(t[i, 11] - t[i, 10]),
                          "bubble_tfull_to_next_mma": int(t[i + 1, 1] - t[i, 5]),
                          "epi_prev_store_end_to_tfull": int(t[i, 5] - t[i - 1, 7]),
                          "prod_tile": int(t[i, 9] - t[i, 8])})
@@ -101,6 +102,64 @@ elif what == "l2hint":
                               "tflops_equiv": round(n * n * k / ms * 1e-9, 2)}), flush=True)
         eng.set("oz_l2hint", 0)
         del A, Cm, buf
+elif what == "collector":
+    # A-collector reuse on/off: timing + bit-identity of the result (integer products are exact, so the two forms must agree exactly)
+    n = 16384
+    eng.set("oz_cluster", 1)
+    for k in (2048, 1024, 512):
+        A, Cm, buf = syrk_setup(n, k)
+        res = {}
+        for on in (0, 1):
+            eng.set("oz_collector", on)
+            Cm.zero_()
+            syrk(buf, n, k, Cm)
+            torch.cuda.synchronize()
+            res[on] = Cm.clone()
+            ms = ev(lambda: syrk(buf, n, k, Cm), reps=5)
+            print(json.dumps({"op": "oz_syrk_collector", "n": n, "K": k, "collector": on, "ms": round(ms, 4),
+                              "tflops_equiv": round(n * n * k / ms * 1e-9, 2)}), flush=True)
+        ref = -(A[:512] @ A[:512].T)
+        print(json.dumps({"op": "oz_collector_identity", "K": k, "bit_identical": bool(torch.equal(res[0], res[1])),
+                          "max_abs_diff": float((res[0] - res[1]).abs().max()),
+                          "max_err_vs_fp64_matmul_512": float((torch.tril(res[1][:512, :512]) - torch.tril(ref)).abs().max())}), flush=True)
+        eng.set("oz_collector", 0)
+        del A, Cm, buf, res
+elif what == "bound":
+    # what bounds the k-loop: the same SYRK with operand loads switched off after the first stages (gemm_cfg 7: MMA + smem reads
+    # only, results are garbage), with the A-collector on/off, and the CTA-0 timeline of each
+    n, k = 16384, 2048
+    eng.set("oz_cluster", 1)
+    A, Cm, buf = syrk_setup(n, k)
+    cap = 120
+    ref = {}
+    for name, cfg, order in (("loads_on_order0", 0, 0), ("loads_on_order1", 0, 1), ("loads_on_order2", 0, 2), ("loads_off_order0", 7, 0),
+                             ("loads_off_order1", 7, 1), ("loads_off_order2", 7, 2)):
+        eng.set("gemm_cfg", cfg); eng.set("oz_order", order)
+        if cfg == 0:
+            Cm.zero_(); syrk(buf, n, k, Cm); torch.cuda.synchronize(); ref[order] = Cm.clone()
+        ms = ev(lambda: syrk(buf, n, k, Cm), reps=5)
+        dbg = torch.zeros(cap * 16, dtype=torch.int64, device=dev)
+        eng.L.bgp_debug_oz_timeline(eng.h, C.c_void_p(dbg.data_ptr()), cap)
+        syrk(buf, n, k, Cm)
+        torch.cuda.synchronize()
+        eng.L.bgp_debug_oz_timeline(eng.h, C.c_void_p(0), 0)
+        t = dbg.view(cap, 16).cpu().numpy()
+        import statistics as st
+        loops = [int(t[i, 3] - t[i, 1]) for i in range(2, 50) if t[i + 1, 1] != 0]
+        per = [int(t[i + 1, 1] - t[i, 1]) for i in range(2, 50) if t[i + 1, 1] != 0]
+        print(json.dumps({"op": "oz_bound", "case": name, "n": n, "K": k, "ms": round(ms, 4), "tflops_equiv": round(n * n * k / ms * 1e-9, 2),
+                          "mma_loop_cycles_per_kblock": round(st.median(loops) / (k / 64), 1), "tile_period_cycles": int(st.median(per))}), flush=True)
+    print(json.dumps({"op": "oz_order_identity", "bit_identical": bool(torch.equal(ref[0], ref[1]) and torch.equal(ref[0], ref[2]))}), flush=True)
+    for kk in (1024, 512):
+        A2, C2, b2 = syrk_setup(n, kk)
+        eng.set("gemm_cfg", 0)
+        for order in (0, 1, 2):
+            eng.set("oz_order", order)
+            ms = ev(lambda: syrk(b2, n, kk, C2), reps=5)
+            print(json.dumps({"op": "oz_syrk_order", "n": n, "K": kk, "order": order, "ms": round(ms, 4), "tflops_equiv": round(n * n * kk / ms * 1e-9, 2)}), flush=True)
+        del A2, C2, b2
+    eng.set("oz_order", 2)
+    eng.set("gemm_cfg", 0); eng.set("oz_collector", 0)
 elif what == "one":
     grp, k = int(sys.argv[2]), int(sys.argv[3])
     n = 16384

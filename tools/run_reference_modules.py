@@ -44,9 +44,15 @@ def find_reference():
     if os.path.exists(TARBALL):
         dst = os.path.join(tempfile.gettempdir(), "battgp_reference_%d" % os.getuid())
         if not os.path.isdir(os.path.join(dst, "src", "batt_models")):
-            os.makedirs(dst, exist_ok=True)
+            # several ranks may get here at once: unpack privately, then publish with one atomic rename
+            tmp = tempfile.mkdtemp(prefix="battgp_reference_unpack_")
             with tarfile.open(TARBALL) as tf:
-                tf.extractall(dst)
+                tf.extractall(tmp, filter="data")
+            try:
+                os.rename(tmp, dst)
+            except OSError:                      # another process published first
+                import shutil
+                shutil.rmtree(tmp, ignore_errors=True)
         return dst
     return None
 
@@ -311,12 +317,20 @@ def run_reference_unit_tests(ref, emit):
         old = sys.path[:]
         sys.path.insert(0, ref)
         try:
+            # the reference's tests draw UNSEEDED random inputs, and tests/gp/test_spatiotemporal_gp.py::test_compare_stgp_rgp
+            # pushes them through pinv(K_b, rcond=1e-8) of a rank-deficient matrix (recursive_gp.py:63): it fails for ~7 % of
+            # the draws even in plain CPU torch (60 draws against the stand-in gpytorch of tests/golden/make_golden.py: 4
+            # failures).  A fixed seed makes the run reproducible; seed 0 passes on that CPU stand-in.
+            import numpy as _np
+            import torch as _torch
+            _np.random.seed(0)
+            _torch.manual_seed(0)
             suite = unittest.defaultTestLoader.loadTestsFromName(mod)
             buf = io.StringIO()
             with warnings.catch_warnings():
                 warnings.simplefilter("ignore")
                 res = unittest.TextTestRunner(stream=buf, verbosity=0).run(suite)
-            r = {"check": "reference unit tests (unmodified, through the shim)", "module": mod, "run": res.testsRun,
+            r = {"check": "reference unit tests (unmodified, through the shim)", "module": mod, "rng_seed": 0, "run": res.testsRun,
                  "failures": [str(t[0]) for t in res.failures], "errors": [str(t[0]) for t in res.errors],
                  "error_text": [t[1][-600:] for t in (res.failures + res.errors)][:4], "skipped": [str(t[0]) for t in res.skipped]}
             r["ok"] = bool(res.wasSuccessful() and res.testsRun > 0)
