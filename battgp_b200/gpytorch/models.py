@@ -219,7 +219,7 @@ class ExactGP(GP):
             noise = float(self.likelihood.noise.detach().reshape(-1)[0])
             n = train_x.shape[0]
             gp = ShardedGP(binding.to_spec(), _stage(train_x, dev), resid, noise, nb=2048 if n >= 100000 else 1024)
-            gp.fit()
+            gp.fit(_stage(xq, dev))          # the first query grid rides through the factorisation (fit once, predict once: battgp_full.py:98-120)
             self.prediction_strategy = (("sharded", sig), gp, kernel)
         gp = self.prediction_strategy[1]
         test_prior = self.forward(*inputs, **kwargs)

@@ -84,6 +84,10 @@ class CudaOps:
     def oz_gemm(self, buf, rows, arow0, brow0, C, K, alpha, tri, roff, coff, tpc=0):
         self.eng.oz_gemm(buf, rows, arow0, buf, rows, brow0, C, K, alpha=alpha, tri=tri, roff=roff, coff=coff, tpc=tpc)
 
+    def oz_gemm_ab(self, bufA, rowsA, bufB, rowsB, brow0, C, K, alpha):
+        """C += alpha A B^T with A and B from two different slice buffers (A from row 0, full rectangle)."""
+        self.eng.oz_gemm(bufA, rowsA, 0, bufB, rowsB, brow0, C, K, alpha=alpha, tri=False, roff=0, coff=0, tpc=0)
+
     def trsv(self, L, dinv, b, trans):
         self.eng.trsv(L, dinv, b, trans)
 
@@ -110,10 +114,21 @@ class ShardedGP:
         self.rows: Dict[int, torch.Tensor] = {}
         self.dinv: Dict[int, torch.Tensor] = {}
         self.alpha: Optional[torch.Tensor] = None
+        # extra rows riding through the factorisation (fit(xq=...)): E = [K(xq, X); y^T], (m + 1) x N, owned by ONE rank; they
+        # take part in every panel solve and trailing update and come out as [V = K_*N L^-T; z^T = (L^-1 y)^T] -- the
+        # sharded form of bgp_potrf_aug: no separate 98-step solve chain for the predictive variance and for z
+        self.E: Optional[torch.Tensor] = None
+        self.e_owner = 0
+        self.xq_aug: Optional[torch.Tensor] = None
         self.bytes_received = 0
         import os as _os
-        self.lookahead = _os.environ.get("BATTGP_SHARDED_LOOKAHEAD", "1") != "0"   # one panel of look-ahead on a side stream (GPU only)
-        self.tpc_long = 4               # tiles per CTA of the long trailing updates while the side stream needs SMs
+        # one panel of look-ahead on a side stream (GPU only).  OFF by default: measured on 8 x B200 at N = 200 000 it is
+        # slower than the serial schedule (4.61 s against 4.48 s; 4.98 / 5.22 s with 16 / 64 tiles per CTA,
+        # profiles/probe_r02_sharded_8gpu_overlap.jsonl) -- the updates have to leave the persistent form so that the side
+        # stream finds SMs, which costs more than the 0.35 s of exchange and diagonal-block latency it hides.
+        self.lookahead = _os.environ.get("BATTGP_SHARDED_LOOKAHEAD", "0") != "0"
+        self.tpc_long = int(_os.environ.get("BATTGP_SHARDED_TPC", "4"))     # tiles per CTA of the long trailing updates while the side stream needs SMs
+        self.tpc_short = int(_os.environ.get("BATTGP_SHARDED_TPC_SHORT", "1"))
         self.profile = False            # True: synchronise after every phase and accumulate seconds in self.phase_s
         self.phase_s: Dict[str, float] = {}
 
@@ -157,6 +172,13 @@ class ShardedGP:
             self.ops.cov_block(self.x[b0:e], self.x[:e], blk)
             blk[:, b0:e].diagonal().add_(self.noise)
             self.rows[i] = blk
+        if self.xq_aug is not None:
+            self.e_owner = self.nblk % self.P                      # the rank that owns the fewest stripes
+            if self.rank == self.e_owner:
+                m = self.xq_aug.shape[0]
+                self.E = self.ops.empty(m + 1, self.N)
+                self.ops.cov_block(self.xq_aug, self.x, self.E[:m])
+                self.E[m].copy_(self.y)
 
     # ---- streams (no-ops for the CPU checker of tests/test_sharded_cpu.py)
     def _cuda(self):
@@ -217,7 +239,7 @@ class ShardedGP:
         info, logdet = ops.scalars()
         nblk = self.nblk
         main, side = self._mk_streams()
-        overlap = side is not None and not self.profile and getattr(self, "lookahead", True)
+        overlap = side is not None and not self.profile and getattr(self, "lookahead", True) and self.xq_aug is None
         if not overlap:
             side = None
         use_oz_all = getattr(ops, "has_oz", False)
@@ -231,6 +253,9 @@ class ShardedGP:
         ev_u2a = [None, None]            # column block k+2 brought up to date with panel k (main)
         ev_u2 = [None, None]             # every update with panel k issued (main): its buffers may be overwritten
         state = {}
+        state_E = {}
+        aug = self.xq_aug is not None    # extra rows ride along (all ranks must then take part in the LAST panel's broadcast too)
+        ozE = None
 
         def record(stream):
             if stream is None:
@@ -258,12 +283,20 @@ class ShardedGP:
                 Lkk.copy_(Akk)
             else:
                 dkk = ops.zeros_vec(ndinv)
-            if k == nblk - 1:
+            if k == nblk - 1 and not aug:
                 return
             t0 = self._tick("diag_potrf", t0)
             self._bcast(Lkk, owner)
             self._bcast(dkk, owner)
             t0 = self._tick("bcast", t0)
+            if self.E is not None:                                 # this rank owns the extra rows: solve their block of panel k
+                Eb = ops.empty(self.E.shape[0], nbk)
+                Eb.copy_(self.E[:, b0k:ek])
+                ops.trsm_rlt(Lkk, dkk, Eb)
+                self.E[:, b0k:ek].copy_(Eb)
+                state_E[k] = Eb
+            if k == nblk - 1:
+                return
             mine = [i for i in self.owned if i > k]
             nrows = sum(self.nbi(i) for i in mine)
             nbelow, cnt_max, idx = self._panel_geometry(k)
@@ -287,7 +320,8 @@ class ShardedGP:
             t0 = self._tick("panel_trsm", t0)
             # exchange: every rank ends up with the whole panel.  The all-gather result is rank-major; the int8 path
             # slices it straight into stripe order (block map), the DMMA path needs a reordered fp64 copy.
-            use_oz = use_oz_all and nbk % 64 == 0 and len(mine) > 0
+            need_panel = len(mine) > 0 or self.E is not None      # this rank updates something with panel k
+            use_oz = use_oz_all and nbk % 64 == 0 and need_panel
             panel = None
             panel_rows = nbelow * NB
             if P > 1:
@@ -295,7 +329,7 @@ class ShardedGP:
                 dist.all_gather_into_tensor(recv, send, group=self.group)
                 self.bytes_received += (P - 1) * cnt_max * NB * nbk * 8
                 t0 = self._tick("allgather", t0)
-                if not mine:
+                if not need_panel:
                     pass                                     # this rank has no stripe below the panel: nothing to update
                 elif use_oz and hasattr(ops, "oz_slice_gather"):
                     ozbufs[b] = ops.oz_slice_gather(recv, panel_rows, self._blkmap(k, idx, recv.device), NB, ozbufs[b])
@@ -322,13 +356,24 @@ class ShardedGP:
             mine, ozb, panel, panel_rows = state.pop(k)
             ek, ek1 = self.e(k), self.e(k + 1)
             ek2 = self.e(k + 2) if k + 2 < nblk else ek1
+            if self.E is not None:
+                # extra rows first (the chain of panel k+1 below solves their next column block): E[:, e_k:] -= P_E P_j^T for
+                # every row j below the panel.  Never concurrent with the look-ahead (it is off when rows ride along).
+                t0 = time.perf_counter()
+                Eb = state_E.pop(k)
+                if ozb is not None:
+                    ozE = ops.oz_slice(Eb, ozE)
+                    ops.oz_gemm_ab(ozE, Eb.shape[0], ozb, panel_rows, 0, self.E[:, ek:], self.nbi(k), -1.0)
+                else:
+                    ops.gemm_nt(Eb, panel[:self.N - ek], self.E[:, ek:], -1.0, 1.0)
+                self._tick("trailing_update", t0)
             # ---- side stream: column block k+1 <- panel k, then the whole chain of panel k+1
             with self._On(side):
                 t0 = time.perf_counter()
                 wait(side, ev_u2a[(k - 1) & 1] if k >= 1 else None)      # block k+1 has received panel k-1 (main)
                 wait(side, ev_u2[(k - 1) & 1] if k >= 1 else None)       # buffers of parity (k+1)&1 are free again
                 for i in mine:
-                    self._update(k, i, ek, min(ek1, self.e(i)), ozb, panel, panel_rows, 1 if overlap else 0)
+                    self._update(k, i, ek, min(ek1, self.e(i)), ozb, panel, panel_rows, self.tpc_short if overlap else 0)
                 self._tick("trailing_update", t0)
                 panel_chain(k + 1)
                 ev_panel[(k + 1) & 1] = record(side)
@@ -336,7 +381,7 @@ class ShardedGP:
             t0 = time.perf_counter()
             wait(main, ev_panel[k & 1])
             for i in mine:
-                self._update(k, i, ek1, min(ek2, self.e(i)), ozb, panel, panel_rows, 1 if overlap else 0)
+                self._update(k, i, ek1, min(ek2, self.e(i)), ozb, panel, panel_rows, self.tpc_short if overlap else 0)
             ev_u2a[k & 1] = record(main)
             for i in mine:
                 self._update(k, i, ek2, self.e(i), ozb, panel, panel_rows, self.tpc_long if overlap else 0)
@@ -382,15 +427,30 @@ class ShardedGP:
         """z = L^-1 y (forward, as a 1-row solve_rlt), alpha = L^-T z (backward with reduced contributions)."""
         ops, P = self.ops, self.P
         zb = {}
-        for i in self.owned:
-            w = ops.empty(1, self.nbi(i))
-            w[0].copy_(self.y[self.b0(i):self.e(i)])
-            zb[i] = w
-        self.solve_rlt(zb, 1)
-        zz = ops.zeros_vec(1)
-        for i in self.owned:
-            ops.rowsumsq(zb[i], zz, True)
-        self._allreduce(zz)
+        if self.xq_aug is not None:
+            # z^T left the factorisation as the last of the extra rows: one broadcast instead of the forward chain
+            z = ops.zeros_vec(self.N)
+            if self.E is not None:
+                z.copy_(self.E[self.E.shape[0] - 1])
+            self._bcast(z, self.e_owner)
+            for i in self.owned:
+                w = ops.empty(1, self.nbi(i))
+                w[0].copy_(z[self.b0(i):self.e(i)])
+                zb[i] = w
+            zrow = ops.empty(1, self.N)
+            zrow[0].copy_(z)
+            zz = ops.zeros_vec(1)
+            ops.rowsumsq(zrow, zz, False)
+        else:
+            for i in self.owned:
+                w = ops.empty(1, self.nbi(i))
+                w[0].copy_(self.y[self.b0(i):self.e(i)])
+                zb[i] = w
+            self.solve_rlt(zb, 1)
+            zz = ops.zeros_vec(1)
+            for i in self.owned:
+                ops.rowsumsq(zb[i], zz, True)
+            self._allreduce(zz)
         self.zz = float(zz.item())
         acc = ops.zeros_vec(self.N)
         alpha = ops.zeros_vec(self.N)
@@ -412,8 +472,12 @@ class ShardedGP:
         self.lml = -0.5 * self.zz - 0.5 * self.logdet - 0.5 * n * math.log(2.0 * math.pi)
         return alpha
 
-    def fit(self):
+    def fit(self, xq: Optional[torch.Tensor] = None):
+        """``xq`` (M query points): K(xq, X) and y ride through the factorisation as extra rows (the sharded bgp_potrf_aug), so
+        that predict(xq) needs no solve chain of its own -- BattGP fits a model and predicts once on one grid
+        (battgp_full.py:98-120)."""
         t0 = time.perf_counter()
+        self.xq_aug = None if xq is None else xq.contiguous()
         self.build()
         t0 = self._tick("build", t0)
         info = self.factor()
@@ -462,11 +526,16 @@ class ShardedGP:
             ops.gemm_nt(w, a, mean, 1.0, 1.0)
         mean = mean[:, 0].contiguous()
         self._allreduce(mean)
-        self.solve_rlt(Wb, m)
         ss = ops.zeros_vec(m)
-        for i in self.owned:
-            ops.rowsumsq(Wb[i], ss, True)
-        self._allreduce(ss)
+        if self.xq_aug is not None and self.xq_aug.shape == xq.shape and torch.equal(self.xq_aug, xq):
+            if self.E is not None:                      # V = K_*N L^-T left the factorisation with the extra rows
+                ops.rowsumsq(self.E[:m], ss, False)
+            self._bcast(ss, self.e_owner)
+        else:
+            self.solve_rlt(Wb, m)
+            for i in self.owned:
+                ops.rowsumsq(Wb[i], ss, True)
+            self._allreduce(ss)
         var = ops.cov_diag(xq) - ss
         if clamp:
             var = var.clamp_min(E.MIN_VARIANCE_F64)
@@ -499,7 +568,7 @@ def _timed_steps(n, nb, rank, world, dev, steps, warmup, verify, phases, e2e=Fal
             xs, ys, xqs = x, y, xq
         gp = ShardedGP(spec, xs, ys, B.NOISE, nb=nb)
         gp.profile = profile
-        gp.fit()
+        gp.fit(xqs)
         t0 = time.perf_counter()
         mean, var = gp.predict(xqs)
         gp._tick("predict", t0)
@@ -571,8 +640,9 @@ def parity(rank, world, dev, checker=None):
     x_np, y_np = synth_field_data(n1, seed=7)
     xq_np = query_grid(x_np, 64)
     gp = ShardedGP(spec, torch.tensor(x_np, device=dev), torch.tensor(y_np, device=dev), B.NOISE, nb=256)
-    gp.fit()
-    mean, var = gp.predict(torch.tensor(xq_np, device=dev))
+    xq1 = torch.tensor(xq_np, device=dev)
+    gp.fit(xq1)
+    mean, var = gp.predict(xq1)
     if rank == 0 and checker is not None:
         mr, vr, lml_ref = checker(x_np, y_np, xq_np)
         o = {"n": n1, "nb": 256, "mean_max_rel": float(np.max(np.abs(mean.cpu().numpy() - mr) / np.abs(mr))),
@@ -587,7 +657,7 @@ def parity(rank, world, dev, checker=None):
     xq_np = query_grid(x_np, B.M_QUERY)
     xd, yd, xqd = (torch.tensor(a, device=dev) for a in (x_np, y_np, xq_np))
     gp = ShardedGP(spec, xd, yd, B.NOISE, nb=1024)
-    gp.fit()
+    gp.fit(xqd)
     mean, var = gp.predict(xqd)
     lml = gp.lml
     del gp
@@ -619,7 +689,7 @@ def bench_object(args, rank: int, world: int, dev: torch.device, checker=None):
     flops = B.algorithmic_flops(n)
     eng = E.get_engine(dev)
     return {"config": {"workload": f"full_gp Wiener+RBF-ARD N={n} block-row-sharded Cholesky over {world} GPU(s), NCCL panel broadcast + "
-                                   f"all-gather, one panel of look-ahead (BASELINE configs[4])",
+                                   f"all-gather, query rows and y riding through the factorisation (BASELINE configs[4])",
                        "n": n, "m_query": B.M_QUERY, "kernel": "wiener+rbf_ard", "nb": r["nb"]},
             "metric": B.METRIC, "value": flops / sec * 1e-9, "unit": "GF/s", "scaling": "strong", "steps": r["steps"], "warmup": r["warmup"],
             "ms_per_step": sec * 1e3, "fit_predict_seconds": sec, "timing": "CUDA events, max over ranks, barrier on both sides",

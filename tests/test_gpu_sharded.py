@@ -16,14 +16,17 @@ def _t(a, dev="cuda:0"):
     return torch.tensor(np.ascontiguousarray(a), dtype=torch.float64, device=dev)
 
 
-@pytest.mark.parametrize("n,nb", [(1000, 256), (3000, 512), (2500, 1024)])
-def test_sharded_single_rank_matches_oracle_and_engine(eng, n, nb):
+@pytest.mark.parametrize("n,nb,aug", [(1000, 256, False), (3000, 512, False), (2500, 1024, False), (3000, 512, True), (2500, 1024, True),
+                                      (4100, 2048, True)])
+def test_sharded_single_rank_matches_oracle_and_engine(eng, n, nb, aug):
+    """aug: K(xq, X) and y ride through the factorisation as extra rows (int8 products for the 64-aligned panels)."""
     from battgp_b200 import engine as E
     from battgp_b200.sharded import ShardedGP
     x, y = orc.synth_field_data(n, seed=5)
     xq = orc.query_grid(x)
-    gp = ShardedGP(E.battgp_spec(), _t(x), _t(y), 2.33e-6, nb=nb).fit()
-    mean, var = gp.predict(_t(xq))
+    xq_t = _t(xq)
+    gp = ShardedGP(E.battgp_spec(), _t(x), _t(y), 2.33e-6, nb=nb).fit(xq_t if aug else None)
+    mean, var = gp.predict(xq_t)
     f = orc.fit(orc.battgp_spec(), x, y, 2.33e-6)
     mr, vr = orc.predict(orc.battgp_spec(), x, f, xq)
     assert abs(gp.lml - f.lml) < 1e-9 * abs(f.lml)
@@ -99,8 +102,11 @@ def _nccl_worker(rank, world, port, n, nb, q):
         from battgp_b200.sharded import ShardedGP
         x, y = orc.synth_field_data(n, seed=5)
         dev = f"cuda:{rank}"
-        gp = ShardedGP(E.battgp_spec(), _t(x, dev), _t(y, dev), 2.33e-6, nb=nb).fit()
-        mean, var = gp.predict(_t(orc.query_grid(x), dev))
+        xq_t = _t(orc.query_grid(x), dev)
+        gp = ShardedGP(E.battgp_spec(), _t(x, dev), _t(y, dev), 2.33e-6, nb=nb).fit(xq_t)      # query rows + y ride along
+        mean, var = gp.predict(xq_t)
+        m2, v2 = gp.predict(xq_t[::3].contiguous())                                               # another grid: solve chain
+        assert torch.allclose(m2, mean[::3], rtol=1e-9, atol=0) and torch.allclose(v2, var[::3], rtol=1e-6, atol=0)
         q.put((rank, gp.lml, mean.cpu().numpy(), var.cpu().numpy(), gp.bytes_received))
     finally:
         dist.destroy_process_group()

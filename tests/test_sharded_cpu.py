@@ -70,7 +70,7 @@ class CheckerOps:
             out.copy_(s)
 
 
-def _worker(rank, world, port, n, nb, q):
+def _worker(rank, world, port, n, nb, q, aug=False):
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)
@@ -81,8 +81,12 @@ def _worker(rank, world, port, n, nb, q):
         xq = orc.query_grid(x, 17)
         spec = orc.battgp_spec()
         gp = ShardedGP(E.battgp_spec(), torch.from_numpy(x), torch.from_numpy(y), 2.33e-6, nb=nb, ops=CheckerOps(spec))
-        gp.fit()
-        mean, var = gp.predict(torch.from_numpy(xq))
+        xq_t = torch.from_numpy(xq)
+        gp.fit(xq_t if aug else None)            # aug: K(xq, X) and y ride through the factorisation as extra rows
+        mean, var = gp.predict(xq_t)
+        if aug:                                  # another grid after an augmented fit: the solve chain is still there
+            m2, v2 = gp.predict(torch.from_numpy(xq[::2].copy()))
+            assert torch.allclose(m2, mean[::2], rtol=1e-9, atol=0) and torch.allclose(v2, var[::2], rtol=1e-7, atol=0)
         owned_ok = all(i % world == rank for i in gp.owned) and sum(1 for _ in gp.owned) in (gp.nblk // world, gp.nblk // world + 1)
         assert gp.residual() < 1e-8
         q.put((rank, gp.lml, gp.alpha.numpy(), mean.numpy(), var.numpy(), owned_ok, gp.bytes_received))
@@ -98,12 +102,13 @@ def _free_port():
     return p
 
 
-@pytest.mark.parametrize("n,nb,world", [(700, 128, 2), (1000, 256, 2), (513, 128, 3)])
-def test_sharded_schedule_matches_oracle_over_gloo(n, nb, world):
+@pytest.mark.parametrize("n,nb,world,aug", [(700, 128, 2, False), (1000, 256, 2, True), (513, 128, 3, False), (513, 128, 3, True),
+                                            (640, 128, 2, True)])
+def test_sharded_schedule_matches_oracle_over_gloo(n, nb, world, aug):
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     port = _free_port()
-    procs = [ctx.Process(target=_worker, args=(r, world, port, n, nb, q)) for r in range(world)]
+    procs = [ctx.Process(target=_worker, args=(r, world, port, n, nb, q, aug)) for r in range(world)]
     for p in procs:
         p.start()
     res = [q.get(timeout=180) for _ in range(world)]
@@ -133,3 +138,12 @@ def test_single_process_schedule_without_process_group():
     f = orc.fit(orc.battgp_spec(), x, y, 2.33e-6)
     assert abs(gp.lml - f.lml) < 1e-9 * abs(f.lml)
     assert gp.owned == [0, 1, 2] and gp.bytes_received == 0
+    # the same with the query rows riding through the factorisation
+    xq = orc.query_grid(x, 11)
+    gp2 = ShardedGP(E.battgp_spec(), torch.from_numpy(x), torch.from_numpy(y), 2.33e-6, nb=128, ops=CheckerOps(orc.battgp_spec()))
+    gp2.fit(torch.from_numpy(xq))
+    mean, var = gp2.predict(torch.from_numpy(xq))
+    mr, vr = orc.predict(orc.battgp_spec(), x, f, xq)
+    assert abs(gp2.lml - f.lml) < 1e-9 * abs(f.lml)
+    np.testing.assert_allclose(mean.numpy(), mr, rtol=1e-7)
+    np.testing.assert_allclose(var.numpy(), vr, rtol=1e-6)
