@@ -12,12 +12,14 @@
 // accumulators with tcgen05.ld, recombines them in fp64 and applies C += alpha * (...).
 // (Round 1 used eight balanced 7-bit digits = 36 products for the same 55 bits.)
 //
-// Kernel structure (persistent, 192 threads, one CTA per SM or a few tiles per CTA):
+// Kernel structure (persistent, 224 threads, one CTA per SM or a few tiles per CTA):
 //   warp 0  : producer   -- cp.async.bulk (TMA bulk engine) copies of pre-swizzled slice tiles into a 2-stage smem ring,
 //                           completion on mbarriers (expect_tx); with clusters the A stage is multicast to the N-adjacent CTAs
 //   warp 1  : MMA issuer -- one elected lane issues 20 wide tcgen05.mma per 64-wide k-block, tcgen05.commit frees the stage
 //   warps 2-5: epilogue  -- software-pipelined tcgen05.ld of the accumulators (one TMEM lane quadrant each), fp64
 //                           recombination, TMEM released, then the C update (C was prefetched into L2 while the MMAs ran)
+//   warp 6  : relay      -- waits on the ring's `full` mbarriers and releases the MMA warp through a named barrier (bar.sync),
+//                           so that the issuing warp never has an mbarrier wait queued behind its UTCIMMAs
 // The slice kernel writes the operand slices to global memory already in the 64-byte-swizzled shared-memory image the
 // UMMA descriptors expect, in [k-block][128-row block][slice] order, so a tile's slices are contiguous bulk copies.
 #include <climits>
@@ -28,6 +30,7 @@ namespace bgp {
 constexpr int OZ_S = 7;
 constexpr int OZ_BM = 128, OZ_BN = 64, OZ_BK = 64;
 constexpr int OZ_STAGES = 2;
+constexpr int OZ_THREADS = 224;                       // warp 0 producer, 1 MMA issuer, 2-5 epilogue, 6 relay (see oz_mma_kernel)
 constexpr int OZ_A_STAGE = OZ_S * OZ_BM * OZ_BK;     // 57344 B
 constexpr int OZ_B_STAGE = OZ_S * OZ_BN * OZ_BK;     // 28672 B
 constexpr int OZ_SLICE_TILE = OZ_BM * OZ_BK;         // 8192 B: one slice of a 128-row block for one k-block
@@ -193,6 +196,7 @@ __device__ __forceinline__ void oz_mma_i8_reuse(uint32_t tmem_d, uint64_t da, ui
                  "tcgen05.mma.cta_group::1.kind::i8.collector::a::lastuse [%0], %1, %2, %3, p;\n\t}"
                  ::"r"(tmem_d), "l"(da), "l"(db), "r"(idesc), "r"(accumulate) : "memory");
 }
+__device__ __forceinline__ void oz_named_sync(int id, int nthreads) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory"); }
 __device__ __forceinline__ void oz_commit(uint32_t bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
@@ -241,6 +245,8 @@ struct OzArgs {
     int tri; int64_t roff, coff;
     int debug_noload;      // experiment: only the first OZ_STAGES k-blocks are really loaded
     int group;             // raster: tile rows per group (oz_decode)
+    int kfence;            // 1: tcgen05.fence::after_thread_sync after every stage wait (0: only after the TMEM-empty wait of a tile)
+    int relay;             // 1: a relay warp watches the `full` barriers and releases the MMA warp through a named barrier
     int order;             // MMA issue order within a k-block: 0 = by A slice, 1 = widest last per k-step, 2 = seven widest last per k-block
     int collector;         // 1: A-collector reuse between the two MMA windows of an A slice
     int l2hint;            // 0: default L2 policy; 1: operand loads evict_last; 2: + streaming C accesses; 3: as 2, no C prefetch
@@ -279,7 +285,7 @@ constexpr int OZ_TBUF = 32 * 33;                  // doubles per epilogue warp (
 // overwritten once EVERY CTA of the cluster has consumed it: the MMA warps commit with a multicast arrive on the `empty`
 // barriers of all CS CTAs (count = CS).  Always grid-stride.
 template <int CS>
-__global__ void __launch_bounds__(192, 1) oz_mma_kernel(OzArgs g, int tiles_m, int tiles_n, int tiles_per_cta) {
+__global__ void __launch_bounds__(OZ_THREADS, 1) oz_mma_kernel(OzArgs g, int tiles_m, int tiles_n, int tiles_per_cta) {
     uint32_t crank = 0;
     if (CS > 1) asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(crank));
     const int tiles_ng = (tiles_n + CS - 1) / CS;               // column groups per tile row
@@ -390,8 +396,13 @@ __global__ void __launch_bounds__(192, 1) oz_mma_kernel(OzArgs g, int tiles_m, i
             for (int kb = 0; kb < KB; kb++, it++) {
                 const int st = it % OZ_STAGES;
                 const uint32_t ph = (it / OZ_STAGES) & 1;
-                mbar_wait(full0 + 8 * st, ph);
-                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                // The stage's `full` barrier is watched by the relay warp (warp 6), which releases this warp through a named
+                // barrier.  An mbarrier wait issued by THIS warp sits in its in-order MIO queue behind the 20 UTCIMMAs of
+                // the previous k-block and stalls the issue of the next ones by 120-250 cycles per k-block; bar.sync does
+                // not (tools/microbench/issue_wait.cu: 2186 vs 2069 cycles per k-block, named barrier = no sync at all).
+                if (g.relay) oz_named_sync(1, 64);
+                else mbar_wait(full0 + 8 * st, ph);
+                if (g.kfence) asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                 if (kb == 0) OZ_STAMP(2);
                 const uint64_t da0 = dzero + (uint64_t)(smem_u32(sA + st * OZ_A_STAGE) >> 4);
                 const uint64_t db0 = dzero + (uint64_t)(smem_u32(sB + st * OZ_B_STAGE) >> 4);
@@ -471,6 +482,19 @@ __global__ void __launch_bounds__(192, 1) oz_mma_kernel(OzArgs g, int tiles_m, i
             }
             OZ_STAMP(3);
             tile_it++;
+        }
+    } else if (warp == 6) {
+        // relay: waits for every stage to be filled (TMA complete_tx on `full`) and hands the MMA warp on through named barrier 1
+        if (g.relay) {
+            uint32_t it = 0;
+            for (int pid = pid_begin; pid < pid_end; pid += pid_step) {
+                int m0, n0;
+                if (!oz_decode<CS>(g, pid, tiles_m, tiles_ng, (int)crank, m0, n0)) continue;
+                for (int kb = 0; kb < KB; kb++, it++) {
+                    mbar_wait(full0 + 8 * (it % OZ_STAGES), (it / OZ_STAGES) & 1);
+                    oz_named_sync(1, 64);
+                }
+            }
         }
     } else {
         const int q = warp & 3;                                   // TMEM lane quadrant this warp may read
@@ -606,6 +630,8 @@ int oz_gemm(Ctx* ctx, const void* bufA, int64_t rowsA_total, int64_t arow0, cons
     g.l2hint = ctx->oz_l2hint;
     g.collector = ctx->oz_collector;
     g.order = ctx->oz_order;
+    g.relay = ctx->oz_relay;
+    g.kfence = ctx->oz_kfence;
     g.brb_max = g.nrb_b - 1;
     g.dbg = ctx->oz_dbg; g.dbg_cap = ctx->oz_dbg_cap;
     const int tiles_m = (int)((M + OZ_BM - 1) / OZ_BM), tiles_n = (int)((N + OZ_BN - 1) / OZ_BN);
@@ -634,7 +660,7 @@ int oz_gemm(Ctx* ctx, const void* bufA, int64_t rowsA_total, int64_t arow0, cons
         if (ncl > total_g) ncl = total_g;
         cudaLaunchConfig_t cfg = {};
         cfg.gridDim = dim3((unsigned)(ncl * cs));
-        cfg.blockDim = dim3(192);
+        cfg.blockDim = dim3(OZ_THREADS);
         cfg.dynamicSmemBytes = SMEM;
         cfg.stream = st;
         cudaLaunchAttribute at[1];
@@ -649,7 +675,7 @@ int oz_gemm(Ctx* ctx, const void* bufA, int64_t rowsA_total, int64_t arow0, cons
     int nfree = nsm - (tpc == 0 ? ctx->oz_reserve_now : 0);
     if (nfree < 1) nfree = 1;
     const int grid = tpc > 0 ? (total + tpc - 1) / tpc : (total < nfree ? total : nfree);
-    oz_mma_kernel<1><<<grid, 192, SMEM, st>>>(g, tiles_m, tiles_n, tpc);
+    oz_mma_kernel<1><<<grid, OZ_THREADS, SMEM, st>>>(g, tiles_m, tiles_n, tpc);
     BGP_LAUNCH_OK(ctx);
     return 0;
 }

@@ -132,8 +132,12 @@ elif what == "bound":
     A, Cm, buf = syrk_setup(n, k)
     cap = 120
     ref = {}
-    for name, cfg, order in (("loads_on_order0", 0, 0), ("loads_on_order1", 0, 1), ("loads_on_order2", 0, 2), ("loads_off_order0", 7, 0),
-                             ("loads_off_order1", 7, 1), ("loads_off_order2", 7, 2)):
+    for name, cfg, order in (("loads_on_order0", 0, 0), ("loads_on_order2", 0, 2), ("loads_on_order2_relay", 0, 12), ("loads_on_order2_nofence", 0, 102),
+                             ("loads_on_order2_relay_nofence", 0, 112), ("loads_off_order2", 7, 2), ("loads_off_order2_relay_nofence", 7, 112)):
+        eng.set("oz_kfence", 0 if order >= 100 else 1)
+        order = order % 100
+        eng.set("oz_relay", 1 if order >= 10 else 0)
+        order = order % 10
         eng.set("gemm_cfg", cfg); eng.set("oz_order", order)
         if cfg == 0:
             Cm.zero_(); syrk(buf, n, k, Cm); torch.cuda.synchronize(); ref[order] = Cm.clone()
@@ -149,16 +153,16 @@ elif what == "bound":
         per = [int(t[i + 1, 1] - t[i, 1]) for i in range(2, 50) if t[i + 1, 1] != 0]
         print(json.dumps({"op": "oz_bound", "case": name, "n": n, "K": k, "ms": round(ms, 4), "tflops_equiv": round(n * n * k / ms * 1e-9, 2),
                           "mma_loop_cycles_per_kblock": round(st.median(loops) / (k / 64), 1), "tile_period_cycles": int(st.median(per))}), flush=True)
-    print(json.dumps({"op": "oz_order_identity", "bit_identical": bool(torch.equal(ref[0], ref[1]) and torch.equal(ref[0], ref[2]))}), flush=True)
+    print(json.dumps({"op": "oz_order_identity", "bit_identical": bool(torch.equal(ref[0], ref[2]))}), flush=True)
     for kk in (1024, 512):
         A2, C2, b2 = syrk_setup(n, kk)
         eng.set("gemm_cfg", 0)
-        for order in (0, 1, 2):
-            eng.set("oz_order", order)
+        for order in (2, 12):
+            eng.set("oz_order", order % 10); eng.set("oz_relay", 1 if order >= 10 else 0)
             ms = ev(lambda: syrk(b2, n, kk, C2), reps=5)
-            print(json.dumps({"op": "oz_syrk_order", "n": n, "K": kk, "order": order, "ms": round(ms, 4), "tflops_equiv": round(n * n * kk / ms * 1e-9, 2)}), flush=True)
+            print(json.dumps({"op": "oz_syrk_order", "n": n, "K": kk, "order": order % 10, "relay": order >= 10, "ms": round(ms, 4), "tflops_equiv": round(n * n * kk / ms * 1e-9, 2)}), flush=True)
         del A2, C2, b2
-    eng.set("oz_order", 2)
+    eng.set("oz_order", 2); eng.set("oz_relay", 1); eng.set("oz_kfence", 1)
     eng.set("gemm_cfg", 0); eng.set("oz_collector", 0)
 elif what == "one":
     grp, k = int(sys.argv[2]), int(sys.argv[3])
