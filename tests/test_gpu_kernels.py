@@ -174,6 +174,109 @@ def test_gemm_nt_i8_ozaki_is_fp64_accurate(eng, M, N, K, tri):
     assert err.max().item() < 4e-16 * 8, err.max().item()
 
 
+def _oz_model(A, B, C0, alpha):
+    """Exact model of csrc/ozaki.cu in Python integers + one rounding per fp64 step of its epilogue: per-row power-of-two
+    scale from the row maximum, q = rint(a 2^(55-e)) cut into seven 8-bit two's-complement digits, the 28 digit-plane products
+    with s + t <= 6 accumulated per class c = s + t as exact integers, fp64 recombination acc = fma(P_c, 2^-8c, acc),
+    tbuf = acc * (alpha 2^eA / 2^14), C = fma(tbuf, 2^eB, C)."""
+    import math
+    from fractions import Fraction
+
+    def slice_rows(X):
+        es, digs = [], []
+        for row in X:
+            mx = max(abs(float(v)) for v in row)
+            e = 0
+            if mx > 0:
+                hi = np.float64(mx).view(np.uint64) >> np.uint64(32)            # the kernel's upper bound from the high word
+                ub = np.uint64((int(hi) << 32) | 0xFFFFFFFF).view(np.float64)
+                f, e = math.frexp(float(ub))
+                if f > 0.99:
+                    e += 1
+            q = [int(np.rint(np.ldexp(float(v), 55 - e))) for v in row]
+            d = []
+            for v in q:                                                        # balanced digits: v = sum_s d_s 256^(6-s), d_s in [-128, 127]
+                ds = []
+                for _ in range(7):
+                    r = ((v + 128) % 256) - 128
+                    ds.append(r)
+                    v = (v - r) // 256
+                d.append(ds[::-1])
+            es.append(e); digs.append(d)
+        return es, np.array(digs, dtype=object)                                  # [rows, K, 7]
+
+    ea, da = slice_rows(A)
+    eb, db = slice_rows(B)
+    out = np.array(C0, dtype=np.float64).copy()
+
+    def rnd(fr):                                                                # Fraction -> nearest double (one rounding)
+        return float(fr)
+
+    for i in range(A.shape[0]):
+        sa = float(alpha) * math.ldexp(1.0, ea[i]) * (1.0 / 16384.0)
+        for j in range(B.shape[0]):
+            P = [0] * 7
+            for s in range(7):
+                for t in range(7 - s):
+                    P[s + t] += int(sum(int(x) * int(y) for x, y in zip(da[i, :, s], db[j, :, t])))
+            acc = float(P[0])
+            for c in range(1, 7):
+                acc = rnd(Fraction(P[c]) * Fraction(1, 1 << (8 * c)) + Fraction(acc))
+            tb = rnd(Fraction(acc) * Fraction(sa))
+            out[i, j] = rnd(Fraction(tb) * Fraction(math.ldexp(1.0, eb[j])) + Fraction(float(out[i, j])))
+    return out
+
+
+def test_gemm_nt_i8_is_bit_identical_to_the_integer_model(eng):
+    """The digit planes, the int32 class sums and the fp64 recombination are deterministic: the GPU result must equal the
+    exact-integer model BIT FOR BIT (the epilogue's constants: 2^-110 = 2^-55 2^-55 is folded as 2^-14 into the A scale
+    and 2^-96 into ... see _oz_model) -- checked on a product small enough for Python integers."""
+    rng = np.random.default_rng(3)
+    M, N, K = 40, 24, 64
+    A = rng.normal(size=(M, K)) * np.exp(2 * rng.normal(size=(M, 1)))
+    B = rng.normal(size=(N, K)) * np.exp(2 * rng.normal(size=(N, 1)))
+    C0 = rng.normal(size=(M, N))
+    Cd = _t(C0)
+    eng.gemm_nt_i8(_t(A), _t(B), Cd, alpha=-1.0)
+    out = Cd.cpu().numpy()
+    # scale bookkeeping of the kernel: a = q 2^(e-55), so a b = q_a q_b 2^(ea+eb-110); class c carries 256^(12-c) = 2^(96-8c);
+    # the epilogue applies 2^-14 with the row scale: 2^(96-110) = 2^-14
+    ref = _oz_model(A, B, C0, -1.0)
+    assert np.array_equal(out, ref), float(np.abs(out - ref).max())
+
+
+def test_int8_kernel_variants_are_bit_identical(eng):
+    """Issue order, relay warp, A-collector, stage fence, L2 hints and the cluster forms only change WHEN things happen; the
+    integer products are exact, so every variant must reproduce the default result bit for bit."""
+    g = torch.Generator().manual_seed(5)
+    n, K = 1536, 512
+    A = torch.randn(n, K, generator=g, dtype=torch.float64) * torch.exp(2 * torch.randn(n, 1, generator=g, dtype=torch.float64))
+    Ad = _t(A.numpy())
+    buf = eng.oz_slice(Ad)
+    defaults = {"oz_order": 2, "oz_relay": 1, "oz_collector": 0, "oz_kfence": 1, "oz_l2hint": 0, "oz_cluster": 1}
+
+    def run(**kw):
+        for k, v in {**defaults, **kw}.items():
+            eng.set(k, v)
+        C = torch.zeros(n, n, dtype=torch.float64, device=Ad.device)
+        eng.oz_gemm(buf, n, 0, buf, n, 0, C, K, alpha=-1.0, tri=True)
+        torch.cuda.synchronize()
+        return C
+
+    try:
+        base = run()
+        ref = -(A @ A.T)
+        low = torch.tril(torch.ones(n, n, dtype=torch.bool))
+        scale = A.abs().amax(1, keepdim=True) * A.abs().amax(1, keepdim=True).T * K
+        assert ((base.cpu() - ref).abs() / scale)[low].max().item() < 4e-16 * 8
+        for kw in ({"oz_order": 0}, {"oz_order": 1}, {"oz_relay": 0}, {"oz_collector": 1, "oz_order": 0}, {"oz_kfence": 0},
+                   {"oz_l2hint": 1}, {"oz_l2hint": 2}, {"oz_cluster": 2}, {"oz_cluster": 4}):
+            assert torch.equal(run(**kw), base), kw
+    finally:
+        for k, v in defaults.items():
+            eng.set(k, v)
+
+
 def test_gemm_nt_i8_special_rows(eng):
     """zero rows, denormal-sized rows, and NaN / Inf rows (poisoned rows must come out NaN as in fp64 arithmetic)."""
     M, N, K = 256, 128, 128

@@ -11,5 +11,6 @@ timeout 300 ncu $F -k regex:oz_mma -s 14 -c 1 -o $OUT/oz_mma_in_potrf python too
 timeout 300 ncu $F -k regex:cov_build -c 1 -o $OUT/cov_build_40k python tools/one_fit.py 40000 > $OUT/ncu_cov.log 2>&1
 timeout 300 ncu $F -k regex:trsv_fwd_step -s 150 -c 1 -o $OUT/trsv_fwd_step_40k python tools/one_fit.py 40000 > $OUT/ncu_trsv.log 2>&1
 timeout 300 ncu $F -k regex:trsv_bwd_step -s 150 -c 1 -o $OUT/trsv_bwd_step_40k python tools/one_fit.py 40000 > $OUT/ncu_trsvb.log 2>&1
-timeout 300 ncu $F -k regex:oz_slice -s 3 -c 1 -o $OUT/oz_slice_40k python tools/one_fit.py 40000 > $OUT/ncu_slice.log 2>&1
+timeout 300 ncu $F -k regex:oz_slice -s 8 -c 1 -o $OUT/oz_slice_40k python tools/one_fit.py 40000 > $OUT/ncu_slice.log 2>&1
 ls -la $OUT
+timeout 300 python -m pytest tests/test_gpu_kernels.py -m gpu -q -k "bit_identical" > $OUT/pytest_new.log 2>&1; tail -3 $OUT/pytest_new.log
