@@ -246,6 +246,7 @@ struct OzArgs {
     int debug_noload;      // experiment: only the first OZ_STAGES k-blocks are really loaded
     int group;             // raster: tile rows per group (oz_decode)
     int kfence;            // 1: tcgen05.fence::after_thread_sync after every stage wait (0: only after the TMEM-empty wait of a tile)
+    int dbg_epi;           // experiments (wrong results): 1 = no store phase, 2 = smem transpose only, 3 = global traffic only
     int relay;             // 1: a relay warp watches the `full` barriers and releases the MMA warp through a named barrier
     int order;             // MMA issue order within a k-block: 0 = by A slice, 1 = widest last per k-step, 2 = seven widest last per k-block
     int collector;         // 1: A-collector reuse between the two MMA windows of an A slice
@@ -543,12 +544,33 @@ __global__ void __launch_bounds__(OZ_THREADS, 1) oz_mma_kernel(OzArgs g, int til
             // its scheduler, so its instruction count is what the store phase costs)
             const int rbase = m0 + q * 32;
             const int r_hi = min(32, g.M - rbase);
+            if (g.dbg_epi == 1) { tile_it++; continue; }                               // experiment: no store phase at all
 #pragma unroll
             for (int h = 0; h < 2; h++) {
+                if (g.dbg_epi == 3) {                                                   // experiment: global traffic without the smem transpose
+                    const int col = n0 + h * 32 + lane;
+                    if (col < g.N && rbase + 32 <= g.M) {
+                        double* cp = g.C + (int64_t)rbase * g.ldc + col;
+                        double cold[32];
+#pragma unroll
+                        for (int r = 0; r < 32; r++) cold[r] = cp[(int64_t)r * g.ldc];
+#pragma unroll
+                        for (int r = 0; r < 32; r++) cp[(int64_t)r * g.ldc] = cold[r] + acc[h][r] * sa;
+                    }
+                    continue;
+                }
                 // TMEM hands a thread one ROW (lane), global memory wants a warp on one row segment: transpose through smem
 #pragma unroll
                 for (int j = 0; j < 32; j++) tbuf[lane * 33 + j] = acc[h][j] * sa;     // row scale applied here
                 __syncwarp();
+                if (g.dbg_epi == 2) {                                                   // experiment: the smem transpose without global traffic
+                    double sum = 0.0;
+#pragma unroll
+                    for (int r = 0; r < 32; r++) sum += tbuf[r * 33 + lane];
+                    if (sum == 12345.678) g.C[0] = sum;
+                    __syncwarp();
+                    continue;
+                }
                 // now lane = column
                 const int col = n0 + h * 32 + lane;
                 const bool cok = col < g.N;
@@ -631,6 +653,7 @@ int oz_gemm(Ctx* ctx, const void* bufA, int64_t rowsA_total, int64_t arow0, cons
     g.collector = ctx->oz_collector;
     g.order = ctx->oz_order;
     g.relay = ctx->oz_relay;
+    g.dbg_epi = ctx->oz_dbg_epi;
     g.kfence = ctx->oz_kfence;
     g.brb_max = g.nrb_b - 1;
     g.dbg = ctx->oz_dbg; g.dbg_cap = ctx->oz_dbg_cap;

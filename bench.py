@@ -426,7 +426,8 @@ def run_gpu(args, n_gpus: int):
                 "potrf": {"ms": pm, "fp64_equivalent_tflops": fp64_equiv, "fp64_dmma_peak_tflops": FP64_DMMA_PEAK_TFLOPS,
                           "fp64_equivalent_over_dmma_peak": fp64_equiv / FP64_DMMA_PEAK_TFLOPS,
                           "int8_tops": OZ_PAIRS * fp64_equiv, "frac_of_int8_peak": OZ_PAIRS * fp64_equiv / pk["sustained"]},
-                "traffic": ncu_traffic("oz_mma_kernel")}
+                "traffic": (ncu_traffic("oz_mma_kernel") or {}).get("dram_bytes_per_launch"),
+                "traffic_source": (ncu_traffic("oz_mma_kernel") or {}).get("source", "no ncu capture of this round committed")}
     else:
         roof = {"bound": "tensor", "kernel": "bgp_potrf (gemm_nt_kernel DMMA.8x8x4 trailing updates + leaf/panel kernels)",
                 "achieved": fp64_equiv, "peak": FP64_DMMA_PEAK_TFLOPS, "unit": "TFLOP/s", "frac": fp64_equiv / FP64_DMMA_PEAK_TFLOPS,

@@ -16,6 +16,11 @@ def family(name: str) -> str:
 
 
 def main():
+    traffic_json = None
+    if "--traffic-json" in sys.argv:
+        i = sys.argv.index("--traffic-json")
+        traffic_json = sys.argv[i + 1]
+        del sys.argv[i:i + 2]
     path = sys.argv[1]
     rows = []
     with open(path, newline="") as f:
@@ -44,6 +49,15 @@ def main():
         n = max(1, len(f["ids"]))
         print(f"{name:<34} launches={n:>5} total_ms={f['ns'] / 1e6:>9.2f} share={100 * f['ns'] / total:>5.1f}% "
               f"avg_us={f['ns'] / n / 1e3:>9.1f} dram_read_GB={f['rd'] / 1e9:>8.2f} dram_write_GB={f['wr'] / 1e9:>8.2f}")
+
+
+    if traffic_json:
+        import json
+        out = {name: {"dram_bytes_per_launch": (f["rd"] + f["wr"]) / max(1, len(f["ids"])), "launches": len(f["ids"]),
+                      "source": "ncu dram__bytes_read.sum + dram__bytes_write.sum averaged over the kernel's launches in " + path}
+               for name, f in per.items()}
+        with open(traffic_json, "w") as fh:
+            json.dump(out, fh, indent=1)
 
 
 if __name__ == "__main__":
