@@ -348,6 +348,7 @@ int bgp_ctx_set(bgp_ctx* p, const char* key, int value) {
     if (!strcmp(key, "oz_cluster")) { if (value != 1 && value != 2 && value != 4) return BGP_E_ARG; c->oz_cluster = value; return 0; }
     if (!strcmp(key, "oz_kfence")) { c->oz_kfence = value ? 1 : 0; return 0; }
     if (!strcmp(key, "oz_dbg_epi")) { if (value < 0 || value > 3) return BGP_E_ARG; c->oz_dbg_epi = value; return 0; }
+    if (!strcmp(key, "oz_backoff")) { c->oz_backoff = value ? 1 : 0; return 0; }
     if (!strcmp(key, "oz_relay")) { c->oz_relay = value ? 1 : 0; return 0; }
     if (!strcmp(key, "oz_order")) { if (value < 0 || value > 2) return BGP_E_ARG; c->oz_order = value; return 0; }
     if (!strcmp(key, "oz_collector")) { c->oz_collector = value ? 1 : 0; return 0; }

@@ -44,6 +44,7 @@ struct Ctx {
     int oz_tpc_gemm = 0;                    // tiles per CTA of stand-alone bgp_oz_gemm calls (0 = fully persistent)
     int oz_kfence = 1;                      // int8 kernel: tcgen05.fence::after_thread_sync after every operand-stage wait
     int oz_dbg_epi = 0;                     // int8 kernel experiments (results are garbage): parts of the epilogue switched off
+    int oz_backoff = 0;                     // int8 kernel: nanosleep back-off in the producer / relay / epilogue barrier polls
     int oz_relay = 1;                       // int8 kernel: relay warp + named barrier instead of an mbarrier wait by the MMA-issuing warp
     int oz_order = 2;                       // int8 kernel: MMA issue order within a k-block (0: by A slice; 1: widest last per k-step; 2: seven N=256 instructions last)
     int oz_collector = 0;                   // int8 kernel: A-collector reuse (UTCIMMA .A_KEEP/.A_REUSE) between the windows of one A slice (measured: no gain -- the kernel is bound by the L2 -> SM fill, not by the shared-memory port)

@@ -151,6 +151,15 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
         if (mbar_try_wait(bar, parity)) return;
     __trap();
 }
+// the same for waits that are expected to be long (the epilogue waiting for a whole tile of MMAs): back off between polls so
+// that the pollers stay out of the MIO queue the UTCIMMAs and their operand reads go through
+__device__ __forceinline__ void mbar_wait_backoff(uint32_t bar, uint32_t parity, uint32_t ns) {
+    for (uint32_t it = 0; it < (1u << 24); ++it) {
+        if (mbar_try_wait(bar, parity)) return;
+        __nanosleep(ns);
+    }
+    __trap();
+}
 __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                  ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
@@ -247,6 +256,7 @@ struct OzArgs {
     int group;             // raster: tile rows per group (oz_decode)
     int kfence;            // 1: tcgen05.fence::after_thread_sync after every stage wait (0: only after the TMEM-empty wait of a tile)
     int dbg_epi;           // experiments (wrong results): 1 = no store phase, 2 = smem transpose only, 3 = global traffic only
+    int backoff;           // 1: producer / relay / epilogue warps sleep between failed polls of their mbarriers
     int relay;             // 1: a relay warp watches the `full` barriers and releases the MMA warp through a named barrier
     int order;             // MMA issue order within a k-block: 0 = by A slice, 1 = widest last per k-step, 2 = seven widest last per k-block
     int collector;         // 1: A-collector reuse between the two MMA windows of an A slice
@@ -346,7 +356,8 @@ __global__ void __launch_bounds__(OZ_THREADS, 1) oz_mma_kernel(OzArgs g, int til
             for (int kb = 0; kb < KB; kb++, it++) {
                 const int st = it % OZ_STAGES;
                 const uint32_t ph = (it / OZ_STAGES) & 1;
-                mbar_wait(empty0 + 8 * st, ph ^ 1);
+                if (g.backoff) mbar_wait_backoff(empty0 + 8 * st, ph ^ 1, 64);
+                else mbar_wait(empty0 + 8 * st, ph ^ 1);
                 if (elect_one()) {
                     if (CS == 1 && g.debug_noload && it >= OZ_STAGES) {
                         asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(full0 + 8 * st) : "memory");
@@ -492,7 +503,8 @@ __global__ void __launch_bounds__(OZ_THREADS, 1) oz_mma_kernel(OzArgs g, int til
                 int m0, n0;
                 if (!oz_decode<CS>(g, pid, tiles_m, tiles_ng, (int)crank, m0, n0)) continue;
                 for (int kb = 0; kb < KB; kb++, it++) {
-                    mbar_wait(full0 + 8 * (it % OZ_STAGES), (it / OZ_STAGES) & 1);
+                    if (g.backoff) mbar_wait_backoff(full0 + 8 * (it % OZ_STAGES), (it / OZ_STAGES) & 1, 32);
+                    else mbar_wait(full0 + 8 * (it % OZ_STAGES), (it / OZ_STAGES) & 1);
                     oz_named_sync(1, 64);
                 }
             }
@@ -514,7 +526,8 @@ __global__ void __launch_bounds__(OZ_THREADS, 1) oz_mma_kernel(OzArgs g, int til
                     if (n0 + i * 16 < g.N && (!g.tri || ((int64_t)n0 + i * 16 + g.coff <= (int64_t)m0 + row_l + g.roff))) prefetch_l2(crow + i * 16);
             }
             if (warp == 2) OZ_STAMP(4);
-            mbar_wait(tfull, tile_it & 1);
+            if (g.backoff) mbar_wait_backoff(tfull, tile_it & 1, 256);
+            else mbar_wait(tfull, tile_it & 1);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             if (warp == 2) OZ_STAMP(5);
             // drain: 2 column halves x 7 accumulators, the TMEM load of step i+1 in flight while step i is recombined
@@ -653,6 +666,7 @@ int oz_gemm(Ctx* ctx, const void* bufA, int64_t rowsA_total, int64_t arow0, cons
     g.collector = ctx->oz_collector;
     g.order = ctx->oz_order;
     g.relay = ctx->oz_relay;
+    g.backoff = ctx->oz_backoff;
     g.dbg_epi = ctx->oz_dbg_epi;
     g.kfence = ctx->oz_kfence;
     g.brb_max = g.nrb_b - 1;

@@ -187,6 +187,34 @@ elif what == "epi":
                               "mma_loop_cycles_per_kblock": round(st.median(loops) / (k / 64), 1), "tile_period_cycles": int(st.median(per))}), flush=True)
         eng.set("oz_dbg_epi", 0)
         del A, Cm, buf
+elif what == "backoff":
+    n = 16384
+    eng.set("oz_cluster", 1)
+    cap = 120
+    import statistics as st
+    for k in (2048, 512):
+        A, Cm, buf = syrk_setup(n, k)
+        ref = None
+        for rep in range(2):
+            for bo in (0, 1):
+                eng.set("oz_backoff", bo)
+                Cm.zero_(); syrk(buf, n, k, Cm); torch.cuda.synchronize()
+                if ref is None: ref = Cm.clone()
+                same = bool(torch.equal(ref, Cm))
+                ms = ev(lambda: syrk(buf, n, k, Cm), reps=5)
+                dbg = torch.zeros(cap * 16, dtype=torch.int64, device=dev)
+                eng.L.bgp_debug_oz_timeline(eng.h, C.c_void_p(dbg.data_ptr()), cap)
+                syrk(buf, n, k, Cm)
+                torch.cuda.synchronize()
+                eng.L.bgp_debug_oz_timeline(eng.h, C.c_void_p(0), 0)
+                t = dbg.view(cap, 16).cpu().numpy()
+                loops = [int(t[i, 3] - t[i, 1]) for i in range(2, 50) if t[i + 1, 1] != 0]
+                per = [int(t[i + 1, 1] - t[i, 1]) for i in range(2, 50) if t[i + 1, 1] != 0]
+                print(json.dumps({"op": "oz_backoff", "backoff": bo, "n": n, "K": k, "ms": round(ms, 4), "tflops_equiv": round(n * n * k / ms * 1e-9, 2),
+                                  "mma_loop_cycles_per_kblock": round(st.median(loops) / (k / 64), 1), "tile_period_cycles": int(st.median(per)),
+                                  "bit_identical": same}), flush=True)
+        eng.set("oz_backoff", 0)
+        del A, Cm, buf
 elif what == "one":
     grp, k = int(sys.argv[2]), int(sys.argv[3])
     n = 16384
