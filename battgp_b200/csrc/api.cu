@@ -296,6 +296,8 @@ int bgp_ctx_create(int device, bgp_ctx** out) {
     int lo = 0, hi = 0;
     BGP_CUDA_OK(cudaDeviceGetStreamPriorityRange(&lo, &hi));
     BGP_CUDA_OK(cudaStreamCreateWithPriority(&c->panel_stream, cudaStreamNonBlocking, hi));
+    BGP_CUDA_OK(cudaStreamCreateWithPriority(&c->leaf_stream, cudaStreamNonBlocking, hi));
+    for (auto& e : c->ev_chain) BGP_CUDA_OK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
     BGP_CUDA_OK(cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming));
     BGP_CUDA_OK(cudaEventCreateWithFlags(&c->ev_join, cudaEventDisableTiming));
     for (auto& e : c->ev_panel) BGP_CUDA_OK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
@@ -312,6 +314,8 @@ void bgp_ctx_destroy(bgp_ctx* p) {
     Ctx* c = reinterpret_cast<Ctx*>(p);
     DeviceGuard guard(c->device);
     if (c->panel_stream) { cudaStreamSynchronize(c->panel_stream); cudaStreamDestroy(c->panel_stream); }
+    if (c->leaf_stream) { cudaStreamSynchronize(c->leaf_stream); cudaStreamDestroy(c->leaf_stream); }
+    for (auto& e : c->ev_chain) if (e) cudaEventDestroy(e);
     if (c->ev_fork) cudaEventDestroy(c->ev_fork);
     if (c->ev_join) cudaEventDestroy(c->ev_join);
     for (auto& e : c->ev_panel) if (e) cudaEventDestroy(e);
@@ -344,6 +348,8 @@ int bgp_ctx_set(bgp_ctx* p, const char* key, int value) {
         if (!strcmp(key, "sched_tail")) { c->sched_tail = value; return 0; }
         return BGP_E_ARG;
     }
+    if (!strcmp(key, "leaf_chain")) { c->leaf_chain = value ? 1 : 0; return 0; }
+    if (!strcmp(key, "leaf_chain_max")) { if (value < 256 || value > 8192) return BGP_E_ARG; c->leaf_chain_max = value; return 0; }
     if (!strcmp(key, "ozaki")) { c->ozaki = value ? 1 : 0; return 0; }
     if (!strcmp(key, "oz_cluster")) { if (value != 1 && value != 2 && value != 4) return BGP_E_ARG; c->oz_cluster = value; return 0; }
     if (!strcmp(key, "oz_kfence")) { c->oz_kfence = value ? 1 : 0; return 0; }

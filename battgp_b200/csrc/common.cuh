@@ -15,6 +15,10 @@ struct Ctx {
     int device = 0;
     cudaStream_t panel_stream = nullptr;    // high priority: panel factorisation (look-ahead)
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+    cudaStream_t leaf_stream = nullptr;     // high priority: off-critical-path updates of the leaf chain (potrf_chain2)
+    cudaEvent_t ev_chain[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    int leaf_chain = 1;                     // diagonal blocks / small matrices (129..leaf_chain_max rows): right-looking leaf chain on two streams
+    int leaf_chain_max = 2048;
     cudaEvent_t ev_panel[2] = {nullptr, nullptr};
     cudaEvent_t ev_trail[3] = {nullptr, nullptr, nullptr};
     int32_t* d_info = nullptr;              // first failing pivot (1-based), INT_MAX when none

@@ -350,10 +350,60 @@ int trsm_rlt_rec(Ctx* ctx, const double* L, int64_t n, int64_t ldl, const double
     return trsm_rlt_rec(ctx, L + n1 * ldl + n1, n2, ldl, dinv + (n1 / LEAF) * (int64_t)LEAF * LEAF, X + n1, m, ldx, st);
 }
 
+// Right-looking Cholesky of an n x n block over its 128-wide leaves on TWO streams (diagonal blocks of the look-ahead
+// factorisation and whole small matrices, where the chain of dependent kernels -- not the flops -- is what takes the time).
+// Per leaf k only this is serial (stream s1):
+//     leaf k (factor + inverse)  ->  the 128 rows of block k+1:  X = A[k+1,k] inv(L_kk)^T  ->  A[k+1,k+1] -= X X^T  ->  leaf k+1
+// Everything else that panel k touches -- the solve of the rows from block k+2 on and the rank-128 update of the blocks
+// below / right of (k+1,k+1) -- runs on the context's second high-priority stream beside leaf k+1 and is only waited for
+// where its results are read (the recursive form puts all of it on the critical path: 24 GEMM launches between the 8
+// leaves of a 1024 block).  ev_chain: [0..1] leaf done, [2..3] X done, [4..5] side update done (by parity of k), [6] fork/join.
+static int potrf_chain2(Ctx* ctx, double* A, int64_t n, int64_t lda, double* dinv, int64_t gofs, cudaStream_t s1) {
+    cudaStream_t s2 = ctx->leaf_stream;
+    const int64_t nl = (n + LEAF - 1) / LEAF;
+    int rc;
+    BGP_CUDA_OK(cudaEventRecord(ctx->ev_chain[6], s1));
+    BGP_CUDA_OK(cudaStreamWaitEvent(s2, ctx->ev_chain[6], 0));
+    for (int64_t k = 0; k < nl; k++) {
+        const int64_t k0 = k * LEAF, nk = (n - k0 < LEAF) ? n - k0 : LEAF;
+        double* dk = dinv + k * (int64_t)LEAF * LEAF;
+        if ((rc = launch_leaf(ctx, A + k0 * lda + k0, lda, (int)nk, dk, gofs + k0, s1))) return rc;
+        if (k == nl - 1) break;
+        const int64_t r1 = k0 + LEAF, n1 = (n - r1 < LEAF) ? n - r1 : LEAF, r2 = r1 + n1;
+        BGP_CUDA_OK(cudaEventRecord(ctx->ev_chain[k & 1], s1));
+        // block (k+1, k) and (k+1, k+1) carry the side stream's updates with panel k-1
+        if (k >= 1) BGP_CUDA_OK(cudaStreamWaitEvent(s1, ctx->ev_chain[4 + ((k - 1) & 1)], 0));
+        {
+            double* X = A + r1 * lda + k0;
+            GemmArgs g{X, lda, dk, LEAF, X, lda, (int)n1, (int)LEAF, (int)LEAF, 1.0, 0.0, 0, 0, 0};
+            if ((rc = gemm_nt_cfg(ctx, g, 2, s1))) return rc;
+            BGP_CUDA_OK(cudaEventRecord(ctx->ev_chain[2 + (k & 1)], s1));
+            GemmArgs u{X, lda, X, lda, A + r1 * lda + r1, lda, (int)n1, (int)n1, (int)LEAF, -1.0, 1.0, 1, 0, 0};
+            if ((rc = gemm_nt(ctx, u, s1))) return rc;
+        }
+        if (r2 < n) {
+            const int64_t m2 = n - r2;
+            BGP_CUDA_OK(cudaStreamWaitEvent(s2, ctx->ev_chain[k & 1], 0));             // inv(L_kk) is there
+            double* X2 = A + r2 * lda + k0;
+            GemmArgs g{X2, lda, dk, LEAF, X2, lda, (int)m2, (int)LEAF, (int)LEAF, 1.0, 0.0, 0, 0, 0};
+            if ((rc = gemm_nt_cfg(ctx, g, 2, s2))) return rc;
+            BGP_CUDA_OK(cudaStreamWaitEvent(s2, ctx->ev_chain[2 + (k & 1)], 0));       // rows of block k+1 solved
+            // rows r2.., columns r1..: lower part only (global column <= global row)
+            GemmArgs u{X2, lda, A + r1 * lda + k0, lda, A + r2 * lda + r1, lda, (int)m2, (int)(n - r1), (int)LEAF, -1.0, 1.0, 1, r2, r1};
+            if ((rc = gemm_nt(ctx, u, s2))) return rc;
+        }
+        BGP_CUDA_OK(cudaEventRecord(ctx->ev_chain[4 + (k & 1)], s2));
+    }
+    BGP_CUDA_OK(cudaEventRecord(ctx->ev_chain[6], s2));
+    BGP_CUDA_OK(cudaStreamWaitEvent(s1, ctx->ev_chain[6], 0));
+    return 0;
+}
+
 // In-place Cholesky of the n x n block at A; gofs = global index of its first row (for info).
 int potrf_rec(Ctx* ctx, double* A, int64_t n, int64_t lda, double* dinv, int64_t gofs, cudaStream_t st) {
     if (n <= 0) return 0;
     if (n <= LEAF) return launch_leaf(ctx, A, lda, (int)n, dinv, gofs, st);
+    if (ctx->leaf_chain && ctx->leaf_stream && n <= ctx->leaf_chain_max) return potrf_chain2(ctx, A, n, lda, dinv, gofs, st);
     const int64_t n1 = split_point(n), n2 = n - n1;
     int rc = potrf_rec(ctx, A, n1, lda, dinv, gofs, st);
     if (rc) return rc;

@@ -409,7 +409,7 @@ if "sched2" in what:
     for k, v in DEF.items(): eng.set(k, v)
     eng.set("nb", 0)
 if "potrf2" in what:
-    # round 2: default schedule at the sizes of the small-N / mid-N targets, A-collector on/off, cuSOLVER (torch) beside it
+    # round 2: default schedule at the sizes of the small-N / mid-N targets, two-stream leaf chain on/off, cuSOLVER (torch) beside it
     spec = E.battgp_spec()
     eng.set("nb", 0); eng.set("lookahead", 1)
     for n in (1024, 2048, 4096, 8192, 16384, 40000):
@@ -417,8 +417,8 @@ if "potrf2" in what:
         xd = torch.tensor(x, device=dev)
         K = E.alloc_matrix(n, n, dev)
         row = {"op": "potrf2", "n": n}
-        for coll in (1, 0):
-            eng.set("oz_collector", coll)
+        for lc in (1, 0, 1, 0):
+            eng.set("leaf_chain", lc)
             best = 1e30
             for r in range(4 if n <= 16384 else 2):
                 eng.cov_build(spec, xd, noise=2.33e-6, symmetric=True, out=K)
@@ -426,9 +426,10 @@ if "potrf2" in what:
                 e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
                 e0.record(); info, ld, dinv = eng.potrf(K); e1.record(); torch.cuda.synchronize()
                 best = min(best, e0.elapsed_time(e1))
-            row[f"ms_collector{coll}"] = round(best, 3); row["info"] = info; row[f"logdet{coll}"] = ld
-        eng.set("oz_collector", 0)
-        row["tflops_equiv"] = round(n ** 3 / 3 / row["ms_collector1"] * 1e-9, 2)
+            key = f"ms_leaf_chain{lc}"
+            row[key] = round(min(best, row.get(key, 1e30)), 3); row["info"] = info; row[f"logdet{lc}"] = ld
+        eng.set("leaf_chain", 1)
+        row["tflops_equiv"] = round(n ** 3 / 3 / row["ms_leaf_chain1"] * 1e-9, 2)
         if n <= 16384:
             eng.cov_build(spec, xd, noise=2.33e-6, symmetric=True, out=K)
             Kc = K[:, :n].clone()
