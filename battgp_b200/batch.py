@@ -103,6 +103,9 @@ class CellBatch:
         while len(self._slots) < min(count, self.max_streams):
             eng = E.Engine(self.device)               # own bgp_ctx: own scratch scalars, safe to run beside the others
             eng.set("pdl", 0)                         # plain stream order inside the captured graph
+            # concurrent cells fill the GPU, so throughput counts, not latency: above ~1.5k rows the panel schedule (wide-K
+            # int8 updates) does less work per cell than one leaf chain over the whole matrix (9 x N=4000: 13.4 vs 14.7 ms)
+            eng.set("chain_whole_max", 1536)
             self._slots.append((eng, torch.cuda.Stream(self.device), E.alloc_matrix(self.n_max + self.m, self.n_max, self.device)))
 
     def _capture(self, spec, noise, sizes, D):

@@ -126,7 +126,9 @@ static int potrf_driver(Ctx* ctx, double* A, int64_t n, int64_t mx, int64_t lda,
     PanelSchedule S;
     make_schedule(ctx, R, n, S);
     const int64_t npanels = S.npanels();
-    if (!ctx->lookahead || npanels <= 2) {
+    // small matrices: one two-stream leaf chain over the whole matrix (potrf_chain2) instead of panels with look-ahead
+    const bool whole_chain = ctx->leaf_chain && R <= ctx->chain_whole_max && n <= ctx->leaf_chain_max;
+    if (!ctx->lookahead || npanels <= 2 || whole_chain) {
         int rc = potrf_rec(ctx, A, n, lda, dinv, 0, mainst);
         if (!rc && mx > 0) rc = trsm_rlt_rec(ctx, A, n, lda, dinv, A + n * lda, mx, lda, mainst);
         return rc;
@@ -349,6 +351,8 @@ int bgp_ctx_set(bgp_ctx* p, const char* key, int value) {
         return BGP_E_ARG;
     }
     if (!strcmp(key, "leaf_chain")) { c->leaf_chain = value ? 1 : 0; return 0; }
+    if (!strcmp(key, "chain_whole_max")) { if (value < 0 || value > 8192) return BGP_E_ARG; c->chain_whole_max = value; return 0; }
+    if (!strcmp(key, "chain_cfg")) { c->chain_cfg = value ? 1 : 0; return 0; }
     if (!strcmp(key, "leaf_chain_max")) { if (value < 256 || value > 8192) return BGP_E_ARG; c->leaf_chain_max = value; return 0; }
     if (!strcmp(key, "ozaki")) { c->ozaki = value ? 1 : 0; return 0; }
     if (!strcmp(key, "oz_cluster")) { if (value != 1 && value != 2 && value != 4) return BGP_E_ARG; c->oz_cluster = value; return 0; }

@@ -18,7 +18,9 @@ struct Ctx {
     cudaStream_t leaf_stream = nullptr;     // high priority: off-critical-path updates of the leaf chain (potrf_chain2)
     cudaEvent_t ev_chain[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     int leaf_chain = 1;                     // diagonal blocks / small matrices (129..leaf_chain_max rows): right-looking leaf chain on two streams
-    int leaf_chain_max = 2048;
+    int chain_cfg = 1;                      // leaf chain: small-tile (many-CTA) forms of the two serial GEMMs between leaves
+    int leaf_chain_max = 5120;
+    int chain_whole_max = 5120;                // matrices up to this many rows (extra rows included) skip the panel schedule: one leaf chain over the whole matrix
     cudaEvent_t ev_panel[2] = {nullptr, nullptr};
     cudaEvent_t ev_trail[3] = {nullptr, nullptr, nullptr};
     int32_t* d_info = nullptr;              // first failing pivot (1-based), INT_MAX when none

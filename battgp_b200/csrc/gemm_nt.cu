@@ -234,7 +234,8 @@ static int launch_cfg(Ctx* ctx, const GemmArgs& g, cudaStream_t st) {
     return 0;
 }
 
-// cfg: 0 auto, 1 = 128x128, 2 = 64x128 (in-place safe for N<=128, short M), 3 = 64x64, 5 = 128x64 (default big);
+// cfg: 0 auto, 1 = 128x128, 2 = 64x128 (in-place safe for N<=128, short M), 3 = 64x64, 5 = 128x64 (default big),
+// 8 = 16x128 and 9 = 32x32 (the two serial GEMMs between the leaves of potrf_chain2: many small CTAs instead of 2-4 big ones);
 // 4..7 are experimental variants selectable through bgp_ctx_set("gemm_cfg", k)
 int gemm_nt_cfg(Ctx* ctx, const GemmArgs& g, int cfg, cudaStream_t st) {
     if (g.M <= 0 || g.N <= 0) return 0;
@@ -252,6 +253,8 @@ int gemm_nt_cfg(Ctx* ctx, const GemmArgs& g, int cfg, cudaStream_t st) {
         case 4: return launch_cfg<128, 128, 32, 32, 16, 4, 1>(ctx, g, st);   // 16 warps
         case 5: return launch_cfg<128, 64, 32, 32, 16, 3, 2>(ctx, g, st);    // 2 CTAs / SM
         case 6: return launch_cfg<128, 128, 64, 32, 32, 3, 1>(ctx, g, st);   // BK = 32
+        case 8: return launch_cfg<16, 128, 16, 32, 16, 3, 1>(ctx, g, st);    // latency form of the in-place leaf solve: 8 CTAs per 128 rows
+        case 9: return launch_cfg<32, 32, 16, 16, 16, 4, 1>(ctx, g, st);     // latency form of a 128 x 128 update: 10-16 CTAs
         default: return launch_cfg<64, 64, 32, 32, 16, 4, 1>(ctx, g, st);
     }
 }

@@ -376,10 +376,10 @@ static int potrf_chain2(Ctx* ctx, double* A, int64_t n, int64_t lda, double* din
         {
             double* X = A + r1 * lda + k0;
             GemmArgs g{X, lda, dk, LEAF, X, lda, (int)n1, (int)LEAF, (int)LEAF, 1.0, 0.0, 0, 0, 0};
-            if ((rc = gemm_nt_cfg(ctx, g, 2, s1))) return rc;
+            if ((rc = gemm_nt_cfg(ctx, g, ctx->chain_cfg ? 8 : 2, s1))) return rc;
             BGP_CUDA_OK(cudaEventRecord(ctx->ev_chain[2 + (k & 1)], s1));
             GemmArgs u{X, lda, X, lda, A + r1 * lda + r1, lda, (int)n1, (int)n1, (int)LEAF, -1.0, 1.0, 1, 0, 0};
-            if ((rc = gemm_nt(ctx, u, s1))) return rc;
+            if ((rc = gemm_nt_cfg(ctx, u, ctx->chain_cfg ? 9 : 0, s1))) return rc;
         }
         if (r2 < n) {
             const int64_t m2 = n - r2;

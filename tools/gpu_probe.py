@@ -440,3 +440,49 @@ if "potrf2" in what:
         print(json.dumps(row), flush=True)
         del K
         torch.cuda.empty_cache()
+
+if "chainwhole" in what:
+    spec = E.battgp_spec()
+    eng.set("nb", 0); eng.set("lookahead", 1); eng.set("leaf_chain", 1)
+    for n in (1536, 2048, 3072, 4096, 6144):
+        x, y = synth_field_data(n, 0)
+        xd = torch.tensor(x, device=dev)
+        K = E.alloc_matrix(n, n, dev)
+        row = {"op": "chainwhole", "n": n}
+        for cw in (0, 8192, 0, 8192):
+            eng.set("leaf_chain_max", 8192 if cw else 5120); eng.set("chain_whole_max", cw)
+            best = 1e30
+            for r in range(4):
+                eng.cov_build(spec, xd, noise=2.33e-6, symmetric=True, out=K)
+                torch.cuda.synchronize()
+                e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+                e0.record(); info, ld, dinv = eng.potrf(K); e1.record(); torch.cuda.synchronize()
+                best = min(best, e0.elapsed_time(e1))
+            key = "ms_whole_chain" if cw else "ms_panels"
+            row[key] = round(min(best, row.get(key, 1e30)), 3); row["info"] = info; row["logdet_" + key] = ld
+        print(json.dumps(row), flush=True)
+        del K
+    eng.set("leaf_chain_max", 5120); eng.set("chain_whole_max", 5120)
+
+if "chaincfg" in what:
+    spec = E.battgp_spec()
+    eng.set("nb", 0); eng.set("lookahead", 1); eng.set("leaf_chain", 1)
+    for n in (1024, 2048, 4096, 8192, 16384):
+        x, y = synth_field_data(n, 0)
+        xd = torch.tensor(x, device=dev)
+        K = E.alloc_matrix(n, n, dev)
+        row = {"op": "chaincfg", "n": n}
+        for cc in (0, 1, 0, 1):
+            eng.set("chain_cfg", cc)
+            best = 1e30
+            for r in range(4):
+                eng.cov_build(spec, xd, noise=2.33e-6, symmetric=True, out=K)
+                torch.cuda.synchronize()
+                e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+                e0.record(); info, ld, dinv = eng.potrf(K); e1.record(); torch.cuda.synchronize()
+                best = min(best, e0.elapsed_time(e1))
+            key = f"ms_chain_cfg{cc}"
+            row[key] = round(min(best, row.get(key, 1e30)), 3); row["info"] = info; row["logdet" + str(cc)] = ld
+        print(json.dumps(row), flush=True)
+        del K
+    eng.set("chain_cfg", 1)
