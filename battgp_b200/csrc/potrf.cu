@@ -33,8 +33,10 @@ __device__ __forceinline__ double warp_potrf32(double* D, double* rdiag, double*
     for (int k = 0; k < 32; k++) a[k] = (k <= lane) ? D[lane * SP + k] : 0.0;
     double my_d = 1.0;
     int fail = 0;
-    // software-pipelined over the pivots: as soon as column j has updated a[j+1], the next pivot's broadcast and rsqrt
-    // (the long-latency part of the chain) are issued, and the remaining updates of column j run underneath them
+    // The chain from one pivot to the next is kept free of shared memory: lane j+1 holds row j+1, so its own column value
+    // l = a[j] rinv gives the next pivot d_{j+1} = a[j+1] - l^2 locally; that is shuffled out and the rsqrt started at once.
+    // The broadcast of the whole column through shared memory (every lane needs l_k of every row k for its rank-1 update)
+    // runs underneath the rsqrt; it recomputes a[j+1] on lane j+1 from the same operands, i.e. to the same bits.
     double d = shfl_d(a[0], 0);
     double rinv = rsqrt(d);
 #pragma unroll
@@ -43,17 +45,16 @@ __device__ __forceinline__ double warp_potrf32(double* D, double* rdiag, double*
         const double l = (lane == j) ? d * rinv : a[j] * rinv;
         a[j] = l;
         if (lane == j) { my_d = d; rdiag[j] = rinv; }
+        double d_next = 1.0, rinv_next = 1.0;
+        if (j + 1 < 32) {
+            d_next = shfl_d(fma(-l, l, a[j + 1]), j + 1);
+            rinv_next = rsqrt(d_next);
+        }
         // broadcast the column through shared memory: every lane then reads l_k with one (conflict-free, broadcast) LDS.64
         colbuf[(j & 1) * 32 + lane] = l;
         __syncwarp();
-        double d_next = 1.0, rinv_next = 1.0;
-        if (j + 1 < 32) {
-            a[j + 1] = fma(-l, colbuf[(j & 1) * 32 + j + 1], a[j + 1]);
-            d_next = shfl_d(a[j + 1], j + 1);
-            rinv_next = rsqrt(d_next);
-        }
 #pragma unroll
-        for (int k = j + 2; k < 32; k++) a[k] = fma(-l, colbuf[(j & 1) * 32 + k], a[k]);
+        for (int k = j + 1; k < 32; k++) a[k] = fma(-l, colbuf[(j & 1) * 32 + k], a[k]);
         d = d_next;
         rinv = rinv_next;
     }
@@ -132,29 +133,28 @@ leaf_potrf_trtri_kernel(double* A, int64_t lda, int n, double* dinv, int32_t* in
     long long t_prev = clock64();
 
     {
-        // 64 threads x double2 cover one 128-wide row; 4 row groups; 8 loads per thread in flight before the first store
+        // 64 threads x double2 cover one 128-wide row; 4 row groups; ALL 32 loads of a thread are in flight before the first
+        // store (one round trip to L2/HBM for the whole 128 x 128 block instead of four)
         const int jc = (tid & 63) * 2, rg = tid >> 6;
         const bool vec = ((lda & 1) == 0) && ((reinterpret_cast<uintptr_t>(A) & 15) == 0);
-        for (int ib = 0; ib < LEAF; ib += 32) {
-            double2 v[8];
+        double2 v[32];
 #pragma unroll
-            for (int u = 0; u < 8; u++) {
-                const int i = ib + u * 4 + rg;
-                v[u] = make_double2(0.0, 0.0);
-                if (i < n && jc <= i) {
-                    const double* p = A + (int64_t)i * lda + jc;
-                    if (vec) v[u] = *reinterpret_cast<const double2*>(p);
-                    else { v[u].x = p[0]; v[u].y = p[1]; }
-                }
+        for (int u = 0; u < 32; u++) {
+            const int i = u * 4 + rg;
+            v[u] = make_double2(0.0, 0.0);
+            if (i < n && jc <= i) {
+                const double* p = A + (int64_t)i * lda + jc;
+                if (vec) v[u] = *reinterpret_cast<const double2*>(p);
+                else { v[u].x = p[0]; v[u].y = p[1]; }
             }
+        }
 #pragma unroll
-            for (int u = 0; u < 8; u++) {
-                const int i = ib + u * 4 + rg;
-                double a0 = (jc <= i) ? v[u].x : 0.0, a1 = (jc + 1 <= i) ? v[u].y : 0.0;
-                if (i >= n) { a0 = (jc == i) ? 1.0 : 0.0; a1 = (jc + 1 == i) ? 1.0 : 0.0; }
-                S[i * SP + jc] = a0;
-                S[i * SP + jc + 1] = a1;
-            }
+        for (int u = 0; u < 32; u++) {
+            const int i = u * 4 + rg;
+            double a0 = (jc <= i) ? v[u].x : 0.0, a1 = (jc + 1 <= i) ? v[u].y : 0.0;
+            if (i >= n) { a0 = (jc == i) ? 1.0 : 0.0; a1 = (jc + 1 == i) ? 1.0 : 0.0; }
+            S[i * SP + jc] = a0;
+            S[i * SP + jc + 1] = a1;
         }
     }
     __syncthreads();
@@ -199,6 +199,7 @@ leaf_potrf_trtri_kernel(double* A, int64_t lda, int n, double* dinv, int32_t* in
     if (tid == 0 && logdet != nullptr) atomicAdd(logdet, logsum);
 
     // write L back (lower triangle only)
+#pragma unroll 8
     for (int idx = tid; idx < n * LEAF; idx += 256) {
         const int i = idx >> 7, j = idx & (LEAF - 1);
         if (j <= i) A[(int64_t)i * lda + j] = S[i * SP + j];
@@ -207,6 +208,7 @@ leaf_potrf_trtri_kernel(double* A, int64_t lda, int n, double* dinv, int32_t* in
     LEAF_CLK(4);
     // ---- inverse: X = L^-1 in place.  Diagonal 32-blocks come from Dg; block column j (2,1,0):
     //      X[r0:, j] = -X_trail * L[r0:, j] * X_jj   with X_trail = inv(L[r0:, r0:]) already in place
+#pragma unroll 8
     for (int idx = tid; idx < 4 * 32 * 32; idx += 256) {
         const int b = idx >> 10, i = (idx >> 5) & 31, j = idx & 31;
         S[(b * 32 + i) * SP + b * 32 + j] = Dg[b * 32 * BP + i * BP + j];
@@ -251,6 +253,7 @@ leaf_potrf_trtri_kernel(double* A, int64_t lda, int n, double* dinv, int32_t* in
         __syncthreads();
     }
     LEAF_CLK(5);
+#pragma unroll 8
     for (int idx = tid; idx < LEAF * LEAF; idx += 256) {
         const int i = idx >> 7, j = idx & (LEAF - 1);
         dinv[idx] = (j <= i) ? S[i * SP + j] : 0.0;
