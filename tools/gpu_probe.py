@@ -486,3 +486,28 @@ if "chaincfg" in what:
         print(json.dumps(row), flush=True)
         del K
     eng.set("chain_cfg", 1)
+
+if "chaingemm" in what:
+    # which tile form should the side-stream rank-128 updates of the leaf chain use?
+    spec = E.battgp_spec()
+    eng.set("nb", 0); eng.set("lookahead", 1); eng.set("leaf_chain", 1)
+    for n in (2048, 4096, 5000):
+        x, y = synth_field_data(n, 0)
+        xd = torch.tensor(x, device=dev)
+        K = E.alloc_matrix(n, n, dev)
+        row = {"op": "chaingemm", "n": n}
+        for rep in range(2):
+            for cfg in (0, 1, 4, 6):
+                eng.set("gemm_cfg", cfg)
+                best = 1e30
+                for r in range(4):
+                    eng.cov_build(spec, xd, noise=2.33e-6, symmetric=True, out=K)
+                    torch.cuda.synchronize()
+                    e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+                    e0.record(); info, ld, dinv = eng.potrf(K); e1.record(); torch.cuda.synchronize()
+                    best = min(best, e0.elapsed_time(e1))
+                key = f"ms_gemm_cfg{cfg}"
+                row[key] = round(min(best, row.get(key, 1e30)), 3)
+        print(json.dumps(row), flush=True)
+        del K
+    eng.set("gemm_cfg", 0)
