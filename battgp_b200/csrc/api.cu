@@ -352,6 +352,7 @@ int bgp_ctx_set(bgp_ctx* p, const char* key, int value) {
     }
     if (!strcmp(key, "leaf_chain")) { c->leaf_chain = value ? 1 : 0; return 0; }
     if (!strcmp(key, "chain_whole_max")) { if (value < 0 || value > 8192) return BGP_E_ARG; c->chain_whole_max = value; return 0; }
+    if (!strcmp(key, "chain_split")) { c->chain_split = value ? 1 : 0; return 0; }
     if (!strcmp(key, "chain_cfg")) { c->chain_cfg = value ? 1 : 0; return 0; }
     if (!strcmp(key, "leaf_chain_max")) { if (value < 256 || value > 8192) return BGP_E_ARG; c->leaf_chain_max = value; return 0; }
     if (!strcmp(key, "ozaki")) { c->ozaki = value ? 1 : 0; return 0; }

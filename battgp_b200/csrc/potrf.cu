@@ -119,7 +119,10 @@ __device__ long long g_leaf_clk[8];
 //   DMMA product by all warps.  A <- L; then L^-1 by block columns (DMMA products) -> dinv (dense 128x128, zeros above
 //   the diagonal).  info: atomicMin of the 1-based global index of the first non-positive pivot.  logdet += log|A|.
 __global__ void __launch_bounds__(256)
-leaf_potrf_trtri_kernel(double* A, int64_t lda, int n, double* dinv, int32_t* info, int64_t gofs, double* logdet) {
+leaf_potrf_trtri_kernel(double* A, int64_t lda, int n, double* dinv, int32_t* info, int64_t gofs, double* logdet, int mode) {
+    // mode 0: factor + full inverse.  The leaf chain (potrf_chain2) splits the two: mode 1 = factor only and store the inverses
+    // of the four diagonal 32-blocks (all the next block's substitution solve needs) into dinv's diagonal sub-blocks;
+    // mode 2 = load the factor and those four blocks back and complete dinv (off the critical path, on the side stream).
     extern __shared__ double sm[];
     double* S = sm;                          // [128][SP]
     double* T = S + LEAF * SP;               // [96][BP]   scratch for the inverse phase
@@ -161,7 +164,15 @@ leaf_potrf_trtri_kernel(double* A, int64_t lda, int n, double* dinv, int32_t* in
     LEAF_CLK(0);
 
     double logsum = 0.0;
-    for (int kb = 0; kb < 4; kb++) {
+    if (mode == 2) {                      // the factor is already in S: fetch the diagonal-block inverses
+#pragma unroll 4
+        for (int idx = tid; idx < 4 * 32 * 32; idx += 256) {
+            const int b = idx >> 10, i = (idx >> 5) & 31, j = idx & 31;
+            Dg[b * 32 * BP + i * BP + j] = dinv[(b * 32 + i) * LEAF + b * 32 + j];
+        }
+        __syncthreads();
+    }
+    for (int kb = 0; kb < 4 && mode != 2; kb++) {
         const int c0 = kb * 32, r0 = c0 + 32, mt = (LEAF - r0) / 8;     // mt row tiles below the diagonal block
         if (warp == 0) {
             int bad;
@@ -196,13 +207,22 @@ leaf_potrf_trtri_kernel(double* A, int64_t lda, int n, double* dinv, int32_t* in
         __syncthreads();
         LEAF_CLK(3);
     }
-    if (tid == 0 && logdet != nullptr) atomicAdd(logdet, logsum);
-
-    // write L back (lower triangle only)
+    if (mode != 2) {
+        if (tid == 0 && logdet != nullptr) atomicAdd(logdet, logsum);
+        // write L back (lower triangle only)
 #pragma unroll 8
-    for (int idx = tid; idx < n * LEAF; idx += 256) {
-        const int i = idx >> 7, j = idx & (LEAF - 1);
-        if (j <= i) A[(int64_t)i * lda + j] = S[i * SP + j];
+        for (int idx = tid; idx < n * LEAF; idx += 256) {
+            const int i = idx >> 7, j = idx & (LEAF - 1);
+            if (j <= i) A[(int64_t)i * lda + j] = S[i * SP + j];
+        }
+        if (mode == 1) {                  // only the diagonal 32-block inverses leave the kernel
+#pragma unroll 4
+            for (int idx = tid; idx < 4 * 32 * 32; idx += 256) {
+                const int b = idx >> 10, i = (idx >> 5) & 31, j = idx & 31;
+                dinv[(b * 32 + i) * LEAF + b * 32 + j] = Dg[b * 32 * BP + i * BP + j];
+            }
+            return;
+        }
     }
     __syncthreads();
     LEAF_CLK(4);
@@ -256,7 +276,8 @@ leaf_potrf_trtri_kernel(double* A, int64_t lda, int n, double* dinv, int32_t* in
 #pragma unroll 8
     for (int idx = tid; idx < LEAF * LEAF; idx += 256) {
         const int i = idx >> 7, j = idx & (LEAF - 1);
-        dinv[idx] = (j <= i) ? S[i * SP + j] : 0.0;
+        // mode 2: the diagonal 32-blocks are already there and may be being read by the next block's solve: leave them alone
+        if (mode != 2 || (i >> 5) != (j >> 5)) dinv[idx] = (j <= i) ? S[i * SP + j] : 0.0;
     }
     __syncthreads();
     LEAF_CLK(6);
@@ -264,7 +285,7 @@ leaf_potrf_trtri_kernel(double* A, int64_t lda, int n, double* dinv, int32_t* in
 
 void leaf_clk_read(long long* out) { cudaMemcpyFromSymbol(out, g_leaf_clk, sizeof(long long) * 8); long long z[8] = {0}; cudaMemcpyToSymbol(g_leaf_clk, z, sizeof(z)); }
 
-static int launch_leaf(Ctx* ctx, double* A, int64_t lda, int n, double* dinv, int64_t gofs, cudaStream_t st) {
+static int launch_leaf(Ctx* ctx, double* A, int64_t lda, int n, double* dinv, int64_t gofs, cudaStream_t st, int mode = 0) {
     constexpr int SMEM = (LEAF * SP + 96 * BP + 4 * 32 * BP) * sizeof(double);
     static thread_local uint64_t attr_done = 0;
     const uint64_t bit = 1ull << (ctx->device & 63);
@@ -273,7 +294,7 @@ static int launch_leaf(Ctx* ctx, double* A, int64_t lda, int n, double* dinv, in
         attr_done |= bit;
     }
     BGP_CUDA_OK(launch_pdl(ctx->pdl && ctx->pdl_chain, leaf_potrf_trtri_kernel, dim3(1), dim3(256), SMEM, st, A, lda, n, dinv, ctx->d_info, gofs,
-                           ctx->d_scal));
+                           ctx->d_scal, mode));
     BGP_LAUNCH_OK(ctx);
     return 0;
 }
@@ -353,6 +374,101 @@ int trsm_rlt_rec(Ctx* ctx, const double* L, int64_t n, int64_t ldl, const double
     return trsm_rlt_rec(ctx, L + n1 * ldl + n1, n2, ldl, dinv + (n1 / LEAF) * (int64_t)LEAF * LEAF, X + n1, m, ldx, st);
 }
 
+// X [m <= 128 rows, 128] <- X L^-T by blocked forward substitution against the 128 x 128 factor L (lower, row-major) and the
+// inverses Dg of its four diagonal 32-blocks (found in the diagonal sub-blocks of `dinv`):
+//     X_b = (X_b - sum_{c<b} X_c L_bc^T) Dg_b^T          b = 0..3
+// The serial solve between two leaves of potrf_chain2: it needs only what the factor-only leaf (mode 1) leaves behind, so the
+// full block inverse stays off the critical path.  One CTA per 16 rows (8 CTAs for a block), 4 warps; warp w owns the
+// 8-column tile w of the 32-column block being solved, for both 8-row tiles.
+constexpr int XP = LEAF + 4;    // pitch of the X rows in shared memory
+__global__ void __launch_bounds__(128)
+leaf_trsm_subst_kernel(double* X, int64_t ldx, int m, const double* L, int64_t ldl, const double* dinv) {
+    extern __shared__ double sm[];
+    double* Ls = sm;                         // [128][SP]  lower triangle of L (upper part never read)
+    double* Xs = Ls + LEAF * SP;             // [16][XP]
+    double* Ys = Xs + 16 * XP;               // [16][BP]
+    double* Dgs = Ys + 16 * BP;              // [4][32][BP]
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int fr = lane >> 2, fk = lane & 3;
+    const int r0 = blockIdx.x * 16;
+    pdl_wait();
+    pdl_launch_dependents();
+    // loads: the factor's lower triangle (double2, 64 lanes per row), the CTA's 16 rows of X, the four diagonal inverses
+    for (int idx = tid; idx < LEAF * (LEAF / 2); idx += 128) {
+        const int i = idx >> 6, j = (idx & 63) * 2;
+        if (j <= i) {
+            const double2 v = *reinterpret_cast<const double2*>(L + (int64_t)i * ldl + j);
+            Ls[i * SP + j] = v.x;
+            Ls[i * SP + j + 1] = v.y;
+        }
+    }
+    for (int idx = tid; idx < 16 * (LEAF / 2); idx += 128) {
+        const int i = idx >> 6, j = (idx & 63) * 2;
+        double2 v = make_double2(0.0, 0.0);
+        if (r0 + i < m) v = *reinterpret_cast<const double2*>(X + (int64_t)(r0 + i) * ldx + j);
+        Xs[i * XP + j] = v.x;
+        Xs[i * XP + j + 1] = v.y;
+    }
+    for (int idx = tid; idx < 4 * 32 * 32; idx += 128) {
+        const int b = idx >> 10, i = (idx >> 5) & 31, j = idx & 31;
+        Dgs[b * 32 * BP + i * BP + j] = dinv[(b * 32 + i) * LEAF + b * 32 + j];
+    }
+    __syncthreads();
+    for (int b = 0; b < 4; b++) {
+        const int c0 = b * 32 + warp * 8;                     // this warp's 8 columns of block b
+        // (i) Y = X_b - sum_{k < 32 b} X[:, k] L[c, k]
+        double acc[2][2];
+#pragma unroll
+        for (int t = 0; t < 2; t++) {
+            acc[t][0] = Xs[(t * 8 + fr) * XP + c0 + 2 * fk];
+            acc[t][1] = Xs[(t * 8 + fr) * XP + c0 + 2 * fk + 1];
+        }
+        double n0[2] = {0.0, 0.0}, n1[2] = {0.0, 0.0};
+        for (int k4 = 0; k4 < b * 32; k4 += 4) {
+            const double bv = Ls[(c0 + fr) * SP + k4 + fk];
+#pragma unroll
+            for (int t = 0; t < 2; t++) dmma_leaf(n0[t], n1[t], Xs[(t * 8 + fr) * XP + k4 + fk], bv);
+        }
+#pragma unroll
+        for (int t = 0; t < 2; t++) {
+            Ys[(t * 8 + fr) * BP + warp * 8 + 2 * fk] = acc[t][0] - n0[t];
+            Ys[(t * 8 + fr) * BP + warp * 8 + 2 * fk + 1] = acc[t][1] - n1[t];
+        }
+        __syncthreads();
+        // (ii) X_b = Y Dg_b^T   (Dg_b lower triangular with explicit zeros above its diagonal)
+        double x0[2] = {0.0, 0.0}, x1[2] = {0.0, 0.0};
+#pragma unroll
+        for (int k4 = 0; k4 < 32; k4 += 4) {
+            const double bv = Dgs[b * 32 * BP + (warp * 8 + fr) * BP + k4 + fk];
+#pragma unroll
+            for (int t = 0; t < 2; t++) dmma_leaf(x0[t], x1[t], Ys[(t * 8 + fr) * BP + k4 + fk], bv);
+        }
+#pragma unroll
+        for (int t = 0; t < 2; t++) {
+            Xs[(t * 8 + fr) * XP + c0 + 2 * fk] = x0[t];
+            Xs[(t * 8 + fr) * XP + c0 + 2 * fk + 1] = x1[t];
+        }
+        __syncthreads();
+    }
+    for (int idx = tid; idx < 16 * (LEAF / 2); idx += 128) {
+        const int i = idx >> 6, j = (idx & 63) * 2;
+        if (r0 + i < m) *reinterpret_cast<double2*>(X + (int64_t)(r0 + i) * ldx + j) = make_double2(Xs[i * XP + j], Xs[i * XP + j + 1]);
+    }
+}
+
+static int launch_trsm_subst(Ctx* ctx, double* X, int64_t ldx, int m, const double* L, int64_t ldl, const double* dinv, cudaStream_t st) {
+    constexpr int SMEM = (LEAF * SP + 16 * XP + 16 * BP + 4 * 32 * BP) * sizeof(double);
+    static thread_local uint64_t attr_done = 0;
+    const uint64_t bit = 1ull << (ctx->device & 63);
+    if (!(attr_done & bit)) {
+        BGP_CUDA_OK(cudaFuncSetAttribute(leaf_trsm_subst_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
+        attr_done |= bit;
+    }
+    BGP_CUDA_OK(launch_pdl(ctx->pdl && ctx->pdl_chain, leaf_trsm_subst_kernel, dim3((m + 15) / 16), dim3(128), SMEM, st, X, ldx, m, L, ldl, dinv));
+    BGP_LAUNCH_OK(ctx);
+    return 0;
+}
+
 // Right-looking Cholesky of an n x n block over its 128-wide leaves on TWO streams (diagonal blocks of the look-ahead
 // factorisation and whole small matrices, where the chain of dependent kernels -- not the flops -- is what takes the time).
 // Per leaf k only this is serial (stream s1):
@@ -364,25 +480,37 @@ int trsm_rlt_rec(Ctx* ctx, const double* L, int64_t n, int64_t ldl, const double
 static int potrf_chain2(Ctx* ctx, double* A, int64_t n, int64_t lda, double* dinv, int64_t gofs, cudaStream_t s1) {
     cudaStream_t s2 = ctx->leaf_stream;
     const int64_t nl = (n + LEAF - 1) / LEAF;
+    const bool split = ctx->chain_split && ((lda & 1) == 0) && ((reinterpret_cast<uintptr_t>(A) & 15) == 0);
     int rc;
     BGP_CUDA_OK(cudaEventRecord(ctx->ev_chain[6], s1));
     BGP_CUDA_OK(cudaStreamWaitEvent(s2, ctx->ev_chain[6], 0));
     for (int64_t k = 0; k < nl; k++) {
         const int64_t k0 = k * LEAF, nk = (n - k0 < LEAF) ? n - k0 : LEAF;
         double* dk = dinv + k * (int64_t)LEAF * LEAF;
-        if ((rc = launch_leaf(ctx, A + k0 * lda + k0, lda, (int)nk, dk, gofs + k0, s1))) return rc;
-        if (k == nl - 1) break;
+        // split form: the leaf on the critical stream only factors (and leaves the four diagonal 32-block inverses); the
+        // full block inverse is completed on the side stream, where its consumers are
+        const bool last = (k == nl - 1);
+        if ((rc = launch_leaf(ctx, A + k0 * lda + k0, lda, (int)nk, dk, gofs + k0, s1, (split && !last) ? 1 : 0))) return rc;
+        if (last) break;
         const int64_t r1 = k0 + LEAF, n1 = (n - r1 < LEAF) ? n - r1 : LEAF, r2 = r1 + n1;
         BGP_CUDA_OK(cudaEventRecord(ctx->ev_chain[k & 1], s1));
         // block (k+1, k) and (k+1, k+1) carry the side stream's updates with panel k-1
         if (k >= 1) BGP_CUDA_OK(cudaStreamWaitEvent(s1, ctx->ev_chain[4 + ((k - 1) & 1)], 0));
         {
             double* X = A + r1 * lda + k0;
-            GemmArgs g{X, lda, dk, LEAF, X, lda, (int)n1, (int)LEAF, (int)LEAF, 1.0, 0.0, 0, 0, 0};
-            if ((rc = gemm_nt_cfg(ctx, g, ctx->chain_cfg ? 8 : 2, s1))) return rc;
+            if (split) {
+                if ((rc = launch_trsm_subst(ctx, X, lda, (int)n1, A + k0 * lda + k0, lda, dk, s1))) return rc;
+            } else {
+                GemmArgs g{X, lda, dk, LEAF, X, lda, (int)n1, (int)LEAF, (int)LEAF, 1.0, 0.0, 0, 0, 0};
+                if ((rc = gemm_nt_cfg(ctx, g, ctx->chain_cfg ? 8 : 2, s1))) return rc;
+            }
             BGP_CUDA_OK(cudaEventRecord(ctx->ev_chain[2 + (k & 1)], s1));
             GemmArgs u{X, lda, X, lda, A + r1 * lda + r1, lda, (int)n1, (int)n1, (int)LEAF, -1.0, 1.0, 1, 0, 0};
             if ((rc = gemm_nt_cfg(ctx, u, ctx->chain_cfg ? 9 : 0, s1))) return rc;
+        }
+        if (split) {                                                                    // complete inv(L_kk) beside the chain
+            BGP_CUDA_OK(cudaStreamWaitEvent(s2, ctx->ev_chain[k & 1], 0));
+            if ((rc = launch_leaf(ctx, A + k0 * lda + k0, lda, (int)nk, dk, gofs + k0, s2, 2))) return rc;
         }
         if (r2 < n) {
             const int64_t m2 = n - r2;

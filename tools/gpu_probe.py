@@ -511,3 +511,26 @@ if "chaingemm" in what:
         print(json.dumps(row), flush=True)
         del K
     eng.set("gemm_cfg", 0)
+
+if "chainsplit" in what:
+    spec = E.battgp_spec()
+    eng.set("nb", 0); eng.set("lookahead", 1); eng.set("leaf_chain", 1); eng.set("chain_cfg", 1)
+    for n in (1000, 1024, 2048, 4096, 8192, 16384, 40000):
+        x, y = synth_field_data(n, 0)
+        xd = torch.tensor(x, device=dev)
+        K = E.alloc_matrix(n, n, dev)
+        row = {"op": "chainsplit", "n": n}
+        for cc in (0, 1, 0, 1):
+            eng.set("chain_split", cc)
+            best = 1e30
+            for r in range(4 if n <= 16384 else 2):
+                eng.cov_build(spec, xd, noise=2.33e-6, symmetric=True, out=K)
+                torch.cuda.synchronize()
+                e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+                e0.record(); info, ld, dinv = eng.potrf(K); e1.record(); torch.cuda.synchronize()
+                best = min(best, e0.elapsed_time(e1))
+            key = f"ms_split{cc}"
+            row[key] = round(min(best, row.get(key, 1e30)), 3); row["info"] = info; row["logdet" + str(cc)] = ld
+        print(json.dumps(row), flush=True)
+        del K
+    eng.set("chain_split", 0)
