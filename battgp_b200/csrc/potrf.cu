@@ -477,6 +477,8 @@ static int launch_trsm_subst(Ctx* ctx, double* X, int64_t ldx, int m, const doub
 // below / right of (k+1,k+1) -- runs on the context's second high-priority stream beside leaf k+1 and is only waited for
 // where its results are read (the recursive form puts all of it on the critical path: 24 GEMM launches between the 8
 // leaves of a 1024 block).  ev_chain: [0..1] leaf done, [2..3] X done, [4..5] side update done (by parity of k), [6] fork/join.
+// chain_split (off: measured no net gain) additionally takes the block inverse off the chain: factor-only leaf (mode 1), solve
+// of block k+1 by blocked substitution (leaf_trsm_subst_kernel), inverse completed on the side stream (mode 2).
 static int potrf_chain2(Ctx* ctx, double* A, int64_t n, int64_t lda, double* dinv, int64_t gofs, cudaStream_t s1) {
     cudaStream_t s2 = ctx->leaf_stream;
     const int64_t nl = (n + LEAF - 1) / LEAF;
