@@ -229,8 +229,7 @@ def _oz_model(A, B, C0, alpha):
 
 def test_gemm_nt_i8_is_bit_identical_to_the_integer_model(eng):
     """The digit planes, the int32 class sums and the fp64 recombination are deterministic: the GPU result must equal the
-    exact-integer model BIT FOR BIT (the epilogue's constants: 2^-110 = 2^-55 2^-55 is folded as 2^-14 into the A scale
-    and 2^-96 into ... see _oz_model) -- checked on a product small enough for Python integers."""
+    exact-integer model of _oz_model BIT FOR BIT -- checked on a product small enough for Python integers."""
     rng = np.random.default_rng(3)
     M, N, K = 40, 24, 64
     A = rng.normal(size=(M, K)) * np.exp(2 * rng.normal(size=(M, 1)))
