@@ -122,7 +122,7 @@ static int potrf_driver(Ctx* ctx, double* A, int64_t n, int64_t mx, int64_t lda,
         int prev;
         PdlChain(Ctx* c_, bool on) : c(c_), prev(c_->pdl_chain) { c->pdl_chain = on ? 1 : 0; }
         ~PdlChain() { c->pdl_chain = prev; }
-    } pdl_chain(ctx, R < 12000);
+    } pdl_chain(ctx, R < ctx->pdl_chain_rows);
     PanelSchedule S;
     make_schedule(ctx, R, n, S);
     const int64_t npanels = S.npanels();
@@ -352,6 +352,7 @@ int bgp_ctx_set(bgp_ctx* p, const char* key, int value) {
     }
     if (!strcmp(key, "leaf_chain")) { c->leaf_chain = value ? 1 : 0; return 0; }
     if (!strcmp(key, "chain_whole_max")) { if (value < 0 || value > 8192) return BGP_E_ARG; c->chain_whole_max = value; return 0; }
+    if (!strcmp(key, "pdl_chain_rows")) { if (value < 0) return BGP_E_ARG; c->pdl_chain_rows = value; return 0; }
     if (!strcmp(key, "chain_split")) { c->chain_split = value ? 1 : 0; return 0; }
     if (!strcmp(key, "chain_cfg")) { c->chain_cfg = value ? 1 : 0; return 0; }
     if (!strcmp(key, "leaf_chain_max")) { if (value < 256 || value > 8192) return BGP_E_ARG; c->leaf_chain_max = value; return 0; }

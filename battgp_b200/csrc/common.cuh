@@ -18,6 +18,7 @@ struct Ctx {
     cudaStream_t leaf_stream = nullptr;     // high priority: off-critical-path updates of the leaf chain (potrf_chain2)
     cudaEvent_t ev_chain[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     int leaf_chain = 1;                     // diagonal blocks / small matrices (129..leaf_chain_max rows): right-looking leaf chain on two streams
+    int pdl_chain_rows = 12000;             // bgp_potrf chains its leaf / DMMA GEMM launches by programmatic dependent launch below this many rows
     int chain_split = 0;                    // leaf chain: factor-only leaf + substitution solve on the chain, block inverse on the side stream (measured: -4 % at N=1024, +6 % at 4096, +3 % at 40k: off)
     int chain_cfg = 1;                      // leaf chain: small-tile (many-CTA) forms of the two serial GEMMs between leaves
     int leaf_chain_max = 5120;

@@ -534,3 +534,27 @@ if "chainsplit" in what:
         print(json.dumps(row), flush=True)
         del K
     eng.set("chain_split", 0)
+
+if "pdlrows" in what:
+    spec = E.battgp_spec()
+    eng.set("nb", 0); eng.set("lookahead", 1)
+    for n in (8192, 16384, 24576, 40000):
+        x, y = synth_field_data(n, 0)
+        xd = torch.tensor(x, device=dev)
+        K = E.alloc_matrix(n, n, dev)
+        row = {"op": "pdlrows", "n": n}
+        for rep in range(2):
+            for pr in (12000, 1000000):
+                eng.set("pdl_chain_rows", pr)
+                best = 1e30
+                for r in range(3 if n <= 16384 else 2):
+                    eng.cov_build(spec, xd, noise=2.33e-6, symmetric=True, out=K)
+                    torch.cuda.synchronize()
+                    e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+                    e0.record(); info, ld, dinv = eng.potrf(K); e1.record(); torch.cuda.synchronize()
+                    best = min(best, e0.elapsed_time(e1))
+                key = f"ms_pdl_rows_{pr}"
+                row[key] = round(min(best, row.get(key, 1e30)), 3); row["info"] = info
+        print(json.dumps(row), flush=True)
+        del K
+    eng.set("pdl_chain_rows", 12000)
