@@ -54,3 +54,31 @@ def test_flop_model():
     r = bench.step_roofline(200000, 4.0, 8, True)
     assert r["bound"] == "tensor" and 0.3 < r["frac"] < 1.0 and r["fp64_equivalent_over_dmma_peak"] > 1.0
     assert bench.OZ_PAIRS == 28
+
+
+def test_roofline_inputs_come_from_committed_measurements(tmp_path):
+    """`roofline.peak` and `roofline.traffic` are read from files measured on the pool (tools/microbench/i8_peak.cu, the ncu
+    launch list), never hard-coded: the int8 peak is the N=256 tcgen05 microbenchmark, the traffic is dram bytes per launch
+    of the dominant kernel as summarised by tools/summarize_launches.py --traffic-json."""
+    sys.path.insert(0, ROOT)
+    import bench
+    pk = bench.int8_peak()
+    assert "DERIVED" not in pk["source"] and 3000.0 < pk["sustained"] <= pk["burst"] < 5000.0
+    t = bench.ncu_traffic("oz_mma_kernel")
+    assert t is not None and t["launches"] > 50 and 1e8 < t["dram_bytes_per_launch"] < 1e10 and "ncu" in t["source"]
+    # the summariser itself on a three-launch list
+    csv = tmp_path / "l.csv"
+    rows = ['"ID","Process ID","Process Name","Host Name","Kernel Name","Context","Stream","Block Size","Grid Size","Device","CC","Section Name","Metric Name","Metric Unit","Metric Value"']
+    for i, (name, ns, rd, wr) in enumerate([("void bgp::oz_mma_kernel<(int)1>(OzArgs)", "1000", "2000", "500"),
+                                            ("void bgp::oz_mma_kernel<(int)1>(OzArgs)", "3000", "4000", "1500"),
+                                            ("bgp::oz_slice_kernel(double)", "10", "64", "56")]):
+        for metric, unit, val in (("dram__bytes_read.sum", "byte", rd), ("dram__bytes_write.sum", "byte", wr), ("gpu__time_duration.sum", "ns", ns)):
+            rows.append(f'"{i}","1","python","h","{name}","1","7","(224, 1, 1)","(148, 1, 1)","0","10.0","Command line profiler metrics","{metric}","{unit}","{val}"')
+    csv.write_text("\n".join(rows) + "\n")
+    out = tmp_path / "t.json"
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "summarize_launches.py"), str(csv), "--traffic-json", str(out)],
+                       capture_output=True, text=True, timeout=60)
+    assert r.returncode == 0, r.stderr
+    d = json.loads(out.read_text())
+    assert d["oz_mma_kernel"]["launches"] == 2 and d["oz_mma_kernel"]["dram_bytes_per_launch"] == 4000.0
+    assert "oz_mma_kernel" in r.stdout and "launches=    2" in r.stdout
